@@ -1,0 +1,33 @@
+"""Development timing probe (not the contract bench): one workload, CUDA-event timing."""
+import argparse, time, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from tpl_b200 import build, scenarios as sc
+from tpl_b200.batched import BatchedOptim
+import copy
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--model", default="mpc_time")
+ap.add_argument("--batch", type=int, default=4096)
+ap.add_argument("--horizon", type=int, default=100)
+ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--reps", type=int, default=5)
+a = ap.parse_args()
+t0 = time.time()
+pb = getattr(sc, a.model)(batch=a.batch, horizon=a.horizon, max_iterations=a.iters, forced=True)
+print(f"generated {a.batch} problems in {time.time()-t0:.1f}s")
+q0 = sc.apply_to_batched(BatchedOptim(build.zoo_library_path(pb.model), batch=pb.batch, horizon_max=pb.horizon), pb)
+print("fp64 peak TFLOP/s:", q0.measure_fp64_tflops())
+x0 = q0._x.clone(); u0 = q0._u.clone()
+st = {k: v.clone() for k, v in q0._status.items()}
+times = []
+for r in range(a.reps):
+    q0._x.copy_(x0); q0._u.copy_(u0)
+    for k, v in st.items(): q0._status[k].copy_(v)
+    torch.cuda.synchronize()
+    q0.update()
+    times.append(q0.runtime)
+print("ms per update:", [f"{t:.3f}" for t in times])
+best = min(times)
+print(f"{a.model} B={a.batch} N={a.horizon} it={a.iters}: {best:.3f} ms -> {a.batch/best*1e3:.3e} solves/s")
+print("iterations", q0.iterations[:8].tolist(), "cost", q0.traj_costs[:4].tolist())

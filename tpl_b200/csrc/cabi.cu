@@ -1,0 +1,204 @@
+// extern "C" entry points declared in include/tplb200.h, compiled once per problem
+// definition:  nvcc -gencode arch=compute_100a,code=sm_100a -DTPLB_MODEL_HEADER='"generated/<name>.cuh"'
+//
+// Host side of the reference's update() (optim.c:1091-1160): the outer
+// augmented-Lagrangian loop and the inner iLQR loop are unrolled into a fixed
+// sequence of kernel launches; per-problem progress (running / trajectory_changed /
+// winner) lives on the device, so no launch depends on a device->host read.
+#include <cstdio>
+#include <cstring>
+
+#include "solver.cuh"
+
+// Internal linkage: several solver libraries (one per problem definition) are loaded
+// into the same process, and their `Model` types must not be merged by the dynamic
+// linker (inline variables would otherwise get process-wide STB_GNU_UNIQUE binding).
+namespace tplb {
+namespace {
+#include TPLB_MODEL_HEADER
+}
+}
+
+using tplb::Model;
+using Dm = tplb::Dims<Model>;
+
+namespace {
+
+thread_local char g_error[256] = "";
+
+int fail(int code, const char* msg) {
+    std::snprintf(g_error, sizeof g_error, "%s", msg);
+    return code;
+}
+
+int check_launch(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        std::snprintf(g_error, sizeof g_error, "%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+int validate(const tplb_batch* q) {
+    if (!q) return fail(TPLB_E_ARG, "batch is NULL");
+    if (q->struct_bytes != (int32_t)sizeof(tplb_batch)) return fail(TPLB_E_ABI, "tplb_batch size mismatch");
+    if (q->batch <= 0 || q->scenes <= 0) return fail(TPLB_E_ARG, "batch and scenes must be positive");
+    if (q->t_max > TPLB_HORIZON_MAX || q->horizon < 1 || q->horizon > q->t_max)
+        return fail(TPLB_E_HORIZON, "horizon must satisfy 1 <= horizon <= t_max <= 299");
+    if (q->opt_start != 0) return fail(TPLB_E_UNSUPPORTED, "opt_start != 0 is not supported");
+    if (!q->x || !q->u || !q->k || !q->K || !q->u_min || !q->u_max || !q->traj_costs || !q->alpha ||
+        !q->mu || !q->iterations || !q->lg_iterations || !q->mu_step || !q->trajectory_changed ||
+        !q->improved || !q->termination_condition || !q->scene_index || !q->workspace)
+        return fail(TPLB_E_ARG, "a required device pointer is NULL");
+    if (Model::C > 0 && (!q->lagrange_multiplier || !q->barrier_weight || !q->lg_mult_limit))
+        return fail(TPLB_E_ARG, "constraint buffers are NULL");
+    if (Model::NUM_SCALARS > 0 && !q->scalars) return fail(TPLB_E_ARG, "scalars is NULL");
+    for (int a = 0; a < Model::NUM_ARRAYS; ++a)
+        if (q->array_len[a] > 0 && !q->arrays[a]) return fail(TPLB_E_ARG, "a parameter array is NULL");
+    if (q->keep_previous && (!q->prev_x || !q->prev_k)) return fail(TPLB_E_ARG, "prev_x/prev_k are NULL");
+    size_t need = 0;
+    tplb::carve<Model>(nullptr, q->batch, q->t_max, &need);
+    if (q->workspace_bytes < need) return fail(TPLB_E_ARG, "workspace too small");
+    return 0;
+}
+
+// thread-per-problem kernels: one warp per block while the batch cannot fill the
+// chip, so the resident warps spread over all 148 SMs
+int problem_block(int B) { return (B <= 148 * 32 * 8) ? 32 : 128; }
+
+const char* const* names(const char* const* a) { return a; }
+
+}  // namespace
+
+extern "C" {
+
+int32_t tplb_abi_version(void) { return TPLB_ABI_VERSION; }
+
+const tplb_model_info* tplb_model(void) {
+    static const tplb_model_info info = {
+        TPLB_ABI_VERSION, Model::X, Model::U, Model::C,
+        Model::NUM_SCALARS, Model::NUM_ARRAYS, Model::NUM_PARAMS,
+        Model::NAME, Model::DEFINITION_SHA1,
+        names(Model::STATE_NAMES), names(Model::ACTION_NAMES), names(Model::SCALAR_NAMES),
+        names(Model::ARRAY_NAMES), names(Model::PARAM_ORDER),
+        Dm::STRIDE, Dm::OFF_FX, Dm::OFF_FU, Dm::OFF_LX, Dm::OFF_LU, Dm::OFF_LXX, Dm::OFF_LUU, Dm::OFF_LUX,
+    };
+    return &info;
+}
+
+const char* tplb_last_error(void) { return g_error; }
+
+size_t tplb_workspace_bytes(int32_t batch, int32_t t_max) {
+    size_t need = 0;
+    tplb::carve<Model>(nullptr, batch, t_max, &need);
+    return need;
+}
+
+void* tplb_workspace_deriv(void* workspace, int32_t batch, int32_t t_max) {
+    return tplb::carve<Model>(workspace, batch, t_max).deriv;
+}
+
+void* tplb_workspace_cand_cost(void* workspace, int32_t batch, int32_t t_max) {
+    return tplb::carve<Model>(workspace, batch, t_max).cand_cost;
+}
+
+int32_t tplb_update(const tplb_batch* qp, void* stream_) {
+    if (int e = validate(qp)) return e;
+    const tplb_batch q = *qp;
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    const tplb::Workspace ws = tplb::carve<Model>(q.workspace, q.batch, q.t_max);
+    const int B = q.batch, T = q.horizon;
+    const int pb = problem_block(B);
+    const dim3 pgrid((B + pb - 1) / pb);
+    const int sb = 128;                                    // stage-parallel kernels
+    const dim3 sgrid((B + sb - 1) / sb, T);
+    constexpr int PB = 32;                                 // problems per line-search block
+
+    tplb::rollout_init_kernel<Model><<<pgrid, pb, 0, st>>>(q);
+
+    int lg = 0;
+    for (; lg < q.max_lg_iterations; ++lg) {
+        tplb::multiplier_kernel<Model><<<dim3(sgrid.x, Model::C > 0 ? T : 1), sb, 0, st>>>(q, ws);
+        for (int s = 0; s < q.max_iterations; ++s) {
+            tplb::linearize_kernel<Model, false><<<sgrid, sb, 0, st>>>(q, ws);
+            if (q.use_quadratic_terms)
+                tplb::backward_kernel<Model><<<pgrid, pb, 0, st>>>(q, ws, s);
+            else
+                tplb::backward_first_order_kernel<Model><<<pgrid, pb, 0, st>>>(q, ws, s);
+            tplb::line_search_kernel<Model, PB><<<(B + PB - 1) / PB, dim3(PB, tplb::kAlphas), 0, st>>>(q, ws);
+            tplb::accept_kernel<Model><<<dim3(sgrid.x, T + 1), sb, 0, st>>>(q, ws);
+        }
+    }
+    tplb::finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(q, lg);
+    return check_launch("tplb_update");
+}
+
+int32_t tplb_linearize(const tplb_batch* qp, void* stream_) {
+    if (int e = validate(qp)) return e;
+    const tplb_batch q = *qp;
+    const tplb::Workspace ws = tplb::carve<Model>(q.workspace, q.batch, q.t_max);
+    const dim3 grid((q.batch + 127) / 128, q.horizon);
+    tplb::linearize_kernel<Model, true><<<grid, 128, 0, static_cast<cudaStream_t>(stream_)>>>(q, ws);
+    return check_launch("tplb_linearize");
+}
+
+int32_t tplb_shift(const tplb_batch* qp, int32_t amount, const int32_t* amounts, void* stream_) {
+    if (int e = validate(qp)) return e;
+    const tplb_batch q = *qp;
+    tplb::shift_kernel<Model><<<(q.batch + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream_)>>>(q, amount, amounts);
+    return check_launch("tplb_shift");
+}
+
+int32_t tplb_dynamics(const tplb_batch* qp, const double* x_in, const double* u_in,
+                      const int32_t* scene_of_point, int32_t n, int32_t t, double dt,
+                      int32_t continuous, double* x_out, void* stream_) {
+    if (!qp || !x_in || !u_in || !x_out || n <= 0) return fail(TPLB_E_ARG, "tplb_dynamics: bad argument");
+    if (qp->struct_bytes != (int32_t)sizeof(tplb_batch)) return fail(TPLB_E_ABI, "tplb_batch size mismatch");
+    const tplb_batch q = *qp;
+    tplb::dynamics_kernel<Model><<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream_)>>>(
+        q, x_in, u_in, scene_of_point, n, t, dt, continuous, x_out);
+    return check_launch("tplb_dynamics");
+}
+
+int32_t tplb_argmin_groups(const double* traj_costs, int32_t groups, int32_t per_group,
+                           double* min_cost, int32_t* arg_min, void* stream_) {
+    if (!traj_costs || !min_cost || !arg_min || groups <= 0 || per_group <= 0)
+        return fail(TPLB_E_ARG, "tplb_argmin_groups: bad argument");
+    const int threads = 128, warps_per_block = threads / 32;
+    tplb::argmin_groups_kernel<<<(groups + warps_per_block - 1) / warps_per_block, threads, 0,
+                                 static_cast<cudaStream_t>(stream_)>>>(traj_costs, groups, per_group, min_cost, arg_min);
+    return check_launch("tplb_argmin_groups");
+}
+
+double tplb_measure_fp64_tflops(int32_t repeats, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1.0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double* sink = nullptr;
+    if (cudaMalloc(&sink, sizeof(double)) != cudaSuccess) return -1.0;
+    const int blocks = sms * 8, threads = 256, inner = 1 << 14;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    tplb::dfma_peak_kernel<<<blocks, threads, 0, st>>>(sink, inner);         // warm-up
+    double best = -1.0;
+    for (int r = 0; r < (repeats > 0 ? repeats : 3); ++r) {
+        cudaEventRecord(e0, st);
+        tplb::dfma_peak_kernel<<<blocks, threads, 0, st>>>(sink, inner);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8.0 * (double)inner * blocks * threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return best;
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// Device helpers the generated model code calls: small powers and the reference's
+// interpolation lookups (/root/reference/library/tpl/optim/templates/optim.c:330-408),
+// including the x86 quirk that a negative sample position selects the LAST sample.
+#pragma once
+
+#include <cstdint>
+
+namespace tplb {
+
+template <typename R> __device__ __forceinline__ R sq(R a) { return a * a; }
+template <typename R> __device__ __forceinline__ R pow3h(R a) { return a * sqrt(a); }
+template <typename R> __device__ __forceinline__ R ipow3(R a) { return a * a * a; }
+template <typename R> __device__ __forceinline__ R ipow4(R a) { R b = a * a; return b * b; }
+template <typename R> __device__ __forceinline__ R ipow5(R a) { R b = a * a; return b * b * a; }
+template <typename R> __device__ __forceinline__ R ipow6(R a) { R b = a * a * a; return b * b; }
+template <typename R> __device__ __forceinline__ R ipow7(R a) { R b = a * a * a; return b * b * a; }
+template <typename R> __device__ __forceinline__ R ipow8(R a) { R b = a * a; b = b * b; return b * b; }
+
+// optim.c:351-352: min(size-1, max(0lu, (size_t)floor(q))).  On x86-64 the
+// double -> size_t conversion of a negative value yields a huge number, so the
+// min() picks size-1; CUDA's conversion would saturate to 0, hence explicit.
+template <typename R>
+__device__ __forceinline__ int sample_index(R v, int n) {
+    if (!(v >= R(0))) return n - 1;
+    if (v >= R(n)) return n - 1;
+    return static_cast<int>(v);
+}
+
+// optim.c:332-338
+template <typename R>
+__device__ __forceinline__ R short_angle_dist(R from, R to) {
+    const R turn = R(3.14159265358979323846) * 2;
+    const R d = fmod(to - from, turn);
+    return fmod(2 * d, turn) - d;
+}
+
+// Parameter view of ONE problem: scalars of its scene and its scene's rows of the
+// parameter arrays.  scalars: [num_scalars][S]; array a: [S][len[a]].
+template <typename R>
+struct ParamView {
+    const R* scalars;
+    const R* const* arrays;
+    const int32_t* len;
+    int32_t num_scenes;
+    int32_t scene;
+
+    __device__ __forceinline__ R scalar(int i) const {
+        return __ldg(scalars + (size_t)i * num_scenes + scene);
+    }
+    __device__ __forceinline__ const R* row(int a) const {
+        return arrays[a] + (size_t)scene * len[a];
+    }
+
+    // optim.c:374-388 (+ initInterp :347-355)
+    __device__ __forceinline__ R lerp(int a, R x0, R dx, R x) const {
+        const int n = len[a];
+        if (n == 0) return R(0);
+        const R q = (x - x0) / dx;
+        const int lo = sample_index(floor(q), n);
+        const int hi = sample_index(ceil(q), n);
+        R w = q - R(lo);
+        w = (R(0) > w) ? R(0) : w;
+        w = (w < R(1)) ? w : R(1);
+        const R* p = row(a);
+        return (R(1) - w) * __ldg(p + lo) + w * __ldg(p + hi);
+    }
+
+    // optim.c:392-406
+    __device__ __forceinline__ R lerp_angle(int a, R x0, R dx, R x) const {
+        const int n = len[a];
+        if (n == 0) return R(0);
+        const R q = (x - x0) / dx;
+        const int lo = sample_index(floor(q), n);
+        const int hi = sample_index(ceil(q), n);
+        R w = q - R(lo);
+        w = (R(0) > w) ? R(0) : w;
+        w = (w < R(1)) ? w : R(1);
+        const R* p = row(a);
+        const R v0 = __ldg(p + lo);
+        return v0 + short_angle_dist(v0, __ldg(p + hi)) * w;
+    }
+
+    // optim.c:357-370
+    __device__ __forceinline__ R box_interp(int a, R dx, R x) const {
+        const int n = len[a];
+        if (n == 0) return R(0);
+        return __ldg(row(a) + sample_index(floor(x / dx), n));
+    }
+
+    // optim.c:330 — the reference indexes unchecked; clamp instead of reading out of bounds
+    __device__ __forceinline__ R array_value(int a, R i) const {
+        const int n = len[a];
+        if (n == 0) return R(0);
+        int j = static_cast<int>(i);
+        j = j < 0 ? 0 : (j >= n ? n - 1 : j);
+        return __ldg(row(a) + j);
+    }
+};
+
+}  // namespace tplb
