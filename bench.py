@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Headline benchmark: batched iLQR solves/sec on B200 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): 4096 independent kinematic-bicycle MPC problems
+(`trajectory_tracking_mpc_time`, X=6, U=2, C=4), N=100 stages, HEUN, 10 forced
+iLQR iterations, fp64, synthetic road / reference-path data seeded per problem.
+A *step* is one `update()` of the whole batch from the same cold start.  With N
+GPUs every rank solves its own 4096 problems (weak scaling, no data-path
+collective) and one final all_gather collects the per-group best costs.
+
+Prints ONE JSON line (see the driver contract): `value` is device-resident
+throughput, `e2e` the same through the public API with host buffers, `roofline`
+the FP64-pipe fraction of the dominant kernel, `cpu_baseline` the reference's own
+CPU solver on this host.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODEL = "trajectory_tracking_mpc_time"
+METRIC = "batched iLQR solves/sec (N=100, fp64)"
+UNIT = "solves/s"
+
+# Algorithmic flops per stage (add/sub/mul/div = 1,
+# interpolation call = 9; transcendental calls are listed separately as "special").
+FLOPS = {
+    "trajectory_tracking_mpc_time": dict(lin=366, bwd=1717, fwd=225, con=9, sp_lin=22, sp_fwd=12),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="problems per GPU")
+    ap.add_argument("--horizon", type=int, default=100)
+    ap.add_argument("--iterations", type=int, default=10)
+    ap.add_argument("--cpu-sample", type=int, default=2048)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md)
+# ---------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------
+# CPU arm: the reference's own solver on the host cores
+# ---------------------------------------------------------------------------------
+def cpu_solver_factory(model):
+    """(factory, kind): the real reference build if oracle/_ref travelled here,
+    else the C restatement."""
+    from oracle import ref
+    Ref = ref.load(model, "fast")
+    if Ref is not None:
+        return Ref, "reference"
+    from oracle import oracle
+    oracle.build_libs()
+    return (lambda: oracle.OracleOptim(model)), "port"
+
+
+def cpu_throughput(pb, n, threads, repeats=1):
+    """solves/s of `n` problems of `pb` on `threads` host threads.  Objects are
+    prepared beforehand; only update() (GIL released, optim.c:1487) is timed."""
+    import copy
+    from concurrent.futures import ThreadPoolExecutor
+    from tpl_b200 import scenarios as sc
+    factory, kind = cpu_solver_factory(pb.model)
+    n = min(n, pb.batch)
+    objs = [sc.apply_to_single(factory(), pb, i) for i in range(n)]
+    best = None
+    chunks = [list(range(i, n, threads)) for i in range(threads)]
+    for _ in range(repeats):
+        work = [copy.deepcopy(o) for o in objs]
+
+        def run(idx):
+            for i in idx:
+                work[i].update()
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=threads) as pool:
+            list(pool.map(run, chunks))
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n / best, kind, n
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tpl_b200 import scenarios as sc
+    cores = os.cpu_count() or 1
+    n = max(cores * 4, 128)
+    pb = sc.mpc_time(batch=n, horizon=a.horizon, max_iterations=a.iterations, forced=True)
+    for _ in range(a.warmup):
+        cpu_throughput(pb, max(cores, 16), cores)
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(a.steps):
+        v, kind, used = cpu_throughput(pb, n, cores)
+        vals.append(v)
+    elapsed = time.perf_counter() - t0
+    value = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * n / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{n}-problem sample per step of: 4096 independent {MODEL} problems, "
+                               f"N={a.horizon}, {a.iterations} forced iLQR iterations, HEUN, fp64",
+                   "flush": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{n} problems per step x {a.steps} steps, one Optim object per problem, "
+                                   f"{cores} threads, update() only"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": elapsed,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tpl_b200 import build, dist as tdist, scenarios as sc
+    from tpl_b200.batched import BatchedOptim
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, T, I = a.batch, a.horizon, a.iterations
+    lib = build.zoo_library_path(MODEL)
+    if not os.path.exists(lib):
+        build.build_zoo([MODEL])
+    pb = sc.mpc_time(batch=B, horizon=T, max_iterations=I, forced=True, seed0=rank * B)
+    opt = sc.apply_to_batched(BatchedOptim(lib, batch=B, horizon_max=T), pb)
+    group = 64                                           # problems per argmin group (multi-start style)
+
+    x0 = opt._x[0].clone()
+    u0 = opt._u.clone()
+
+    def reset():
+        opt._x[0].copy_(x0)
+        opt._u.copy_(u0)
+        opt.mu = 0.0
+        opt.mu_step = 0
+
+    def step():
+        reset()
+        opt.update()
+        if world > 1:
+            mn, am = opt.argmin_groups(group)
+            tdist.gather_best(mn, am, rank * B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for _ in range(a.steps):
+            step()
+        e1.record()
+        barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = world * B * a.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers --------------------------
+    host = {
+        "x0": torch.from_numpy(pb.x0).pin_memory(),
+        "u0": torch.from_numpy(pb.u0).pin_memory(),
+        "arrays": {k: torch.from_numpy(v).pin_memory() for k, v in pb.arrays.items()},
+        "scalars": {k: torch.from_numpy(v).pin_memory() for k, v in pb.scalars.items()},
+    }
+    out_x = torch.empty((B, T + 1, opt.X), dtype=torch.float64).pin_memory()
+    out_u = torch.empty((B, T, opt.U), dtype=torch.float64).pin_memory()
+    out_c = torch.empty((B,), dtype=torch.float64).pin_memory()
+    out_i = torch.empty((2, B), dtype=torch.int32).pin_memory()
+    h2d = (host["x0"].numel() + host["u0"].numel()) * 8 + sum(v.numel() * 8 for v in host["arrays"].values()) \
+        + sum(v.numel() * 8 for v in host["scalars"].values())
+    d2h = (out_x.numel() + out_u.numel() + out_c.numel()) * 8 + out_i.numel() * 4
+
+    def step_e2e():
+        for k, v in host["scalars"].items():
+            setattr(opt.params, k, v.to(dev, non_blocking=True))
+        for k, v in host["arrays"].items():
+            setattr(opt.params, k, v.to(dev, non_blocking=True))
+        opt.set_initial_state(host["x0"].to(dev, non_blocking=True))
+        opt.u = host["u0"].to(dev, non_blocking=True)
+        opt.mu = 0.0
+        opt.mu_step = 0
+        opt.update()
+        out_x.copy_(opt.x, non_blocking=True)
+        out_u.copy_(opt.u, non_blocking=True)
+        out_c.copy_(opt.traj_costs, non_blocking=True)
+        out_i[0].copy_(opt.iterations, non_blocking=True)
+        out_i[1].copy_(opt.termination_condition, non_blocking=True)
+        if world > 1:
+            mn, am = opt.argmin_groups(group)
+            tdist.gather_best(mn, am, rank * B)
+
+    for _ in range(max(1, a.warmup // 2)):
+        step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * B * a.steps / (e2e_ms * 1e-3)
+
+    # ---- attribution: time per kernel class and algorithmic work (rank 0) ----------------
+    line = None
+    if rank == 0:
+        reset()
+        prof = opt.update_profiled()
+        torch.cuda.synchronize()
+        lin, bwd, roll = (int(c.sum().item()) for c in opt.work_counters())
+        F = FLOPS[MODEL]
+        flops = {
+            "linearize": lin * T * F["lin"],
+            "backward": bwd * T * F["bwd"],
+            "line_search": (roll - B) * T * F["fwd"],
+            "rollout_init": B * T * F["fwd"],
+            "multiplier": B * T * F["con"] * pb.max_lg_iterations,
+        }
+        flops_step = sum(flops.values())
+        launches = sum(c for _, c in prof.values())
+        total_prof_ms = sum(ms for ms, _ in prof.values())
+        dom = max(prof, key=lambda k: prof[k][0])
+        dom_ms, dom_n = prof[dom]
+        peak = opt.measure_fp64_tflops()
+        achieved = flops.get(dom, 0) / (dom_ms * 1e-3) / 1e12
+        ms_per_step = elapsed_ms / a.steps
+        step_tf = flops_step / (ms_per_step * 1e-3) / 1e12
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fd:
+                hbm_peak = json.load(fd)["hbm_gbs"]
+        except (OSError, KeyError, ValueError):
+            hbm_peak = 6650.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"{B} independent {MODEL} problems per GPU (X=6,U=2,C=4), N={T}, "
+                            f"{I} forced iLQR iterations, HEUN, fp64 (BASELINE.json configs[1])",
+                "problems_per_gpu": B, "stages": T, "iterations": I,
+                "flush": "working set per step (derivative blocks + 8 line-search candidates, "
+                         f"{opt._workspace_bytes / 1e6:.0f} MB) exceeds the 126 MB L2; no explicit flush",
+                "final_collective": "all_gather of per-group (min cost, argmin)" if world > 1 else "none (1 GPU)",
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / a.steps},
+            "gpu_launches": launches * a.steps,
+            "gpu_launches_per_step": launches,
+            "roofline": {
+                "bound": "fp64", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                "peak_source": "DFMA loop measured live by tplb_measure_fp64_tflops (MEASURED_PEAKS.json has no fp64 entry)",
+                "algorithmic_flops_per_launch": flops.get(dom, 0) / max(dom_n, 1),
+                "avg_launch_ms": dom_ms / max(dom_n, 1),
+                "special_function_calls_excluded": True,
+            },
+            "roofline_step": {"achieved": step_tf, "peak": peak, "unit": "TFLOP/s",
+                              "frac": step_tf / peak if peak > 0 else None,
+                              "algorithmic_flops_per_solve": flops_step / B},
+            "kernel_ms": {k: round(ms, 4) for k, (ms, _) in prof.items()},
+            "kernel_share": {k: round(ms / total_prof_ms, 4) for k, (ms, _) in prof.items()},
+            "work_per_solve": {"linearisations": lin / B, "backward_sweeps": bwd / B, "rollouts": roll / B},
+            "hbm": {"peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json"},
+            "clocks": clk.summary(),
+        }
+        if world == 1:
+            cores = os.cpu_count() or 1
+            cpu_v, kind, used = cpu_throughput(pb, a.cpu_sample, cores)
+            line["cpu_baseline"] = {
+                "value": cpu_v, "unit": UNIT, "cores": cores, "kind": kind,
+                "sample": f"first {used} problems of the same batch, one Optim object per problem, "
+                          f"{cores} threads, update() only (GIL released)"}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def main():
+    a = parse()
+    world_env = int(os.environ.get("WORLD_SIZE", "0"))
+    if a.gpus > 1 and world_env == 0:
+        # convenience: re-launch one rank per GPU like the driver does
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -12,7 +12,7 @@
  *   Optim.shift(n)        optim.c:1496-1510  ->    tplb_shift()
  *   Optim.dynamics()      optim.c:1512-1581  ->    tplb_dynamics(continuous = 0)
  *   Optim.ct_dynamics()   optim.c:1583-1652  ->    tplb_dynamics(continuous = 1)
- *   array getters fx..lux optim.c:1663-1669  ->    tplb_linearize() fills the same blocks
+ *   array getters fx..lux optim.c:1663-1669  ->    tplb_expand_derivatives() / tplb_linearize()
  *   struct Optim          optim.c:508-622    ->    tplb_batch (device pointers, SoA)
  *   struct Params/DynArray optim.c:297-328   ->    tplb_batch.scalars / .arrays
  *
@@ -70,8 +70,10 @@ typedef struct {
     const char* const* scalar_names;       /* [num_scalars] */
     const char* const* array_names;        /* [num_arrays] */
     const char* const* param_order;        /* [num_params] declaration order */
-    int32_t deriv_stride;                  /* doubles per stage in tplb_batch.deriv */
-    int32_t off_fx, off_fu, off_lx, off_lu, off_lxx, off_luu, off_lux;   /* offsets in a stage block */
+    int32_t deriv_stride;                  /* doubles per stage of a DENSE derivative record */
+    int32_t off_fx, off_fu, off_lx, off_lu, off_lxx, off_luu, off_lux;   /* offsets in a dense record */
+    int32_t deriv_compact;                 /* doubles per stage actually stored by the solver */
+    int32_t num_stage_consts;              /* per-(scene, stage) constants hoisted out of the kernels */
 } tplb_model_info;
 
 /* One batch of B independent problems sharing horizon and solver settings.
@@ -128,12 +130,19 @@ typedef struct {
     int32_t array_len[TPLB_MAX_ARRAYS];
 
     /* scratch owned by the caller, sized by tplb_workspace_bytes():
-     *   deriv      [t_max][deriv_stride][B]  fx,fu,lx,lu,lxx,luu,lux of every stage
-     *   cand_x     [8][t_max+1][X][B]        line-search candidates (next_x of each alpha)
-     *   cand_u     [8][t_max][U][B]
-     *   cand_cost  [8][B], winner [B], running [B]                                         */
+     *   stage_consts [t_max+1][num_stage_consts][S]  interpolation lookups that depend on the stage only
+     *   deriv        [t_max][deriv_compact][B]  the entries of fx,fu,lx,lu,lxx,luu,lux that are not
+     *                                           identically 0 or 1 for this problem definition
+     *   cand_x       [8][t_max+1][X][B]         line-search candidates (next_x of each alpha)
+     *   cand_u       [8][t_max][U][B]
+     *   cost_terms   [8][t_max+1][B]            stage / end cost of every candidate and stage
+     *   cand_cost    [8][B], winner [B], running [B], counters [3][B]                      */
     void* workspace;
     size_t workspace_bytes;
+
+    /* optional: dense derivative records [t_max][deriv_stride][B] in the reference's layout
+     * fx|fu|lx|lu|lxx|luu|lux (row-major each); written only by tplb_expand_derivatives() */
+    double* deriv_dense;
 } tplb_batch;
 
 TPLB_API int32_t tplb_abi_version(void);
@@ -141,11 +150,15 @@ TPLB_API const tplb_model_info* tplb_model(void);
 TPLB_API const char* tplb_last_error(void);
 
 /* Bytes of device scratch a batch of this shape needs. */
-TPLB_API size_t tplb_workspace_bytes(int32_t batch, int32_t t_max);
-/* Device address of the derivative blocks inside a workspace (for fx..lux views). */
-TPLB_API void* tplb_workspace_deriv(void* workspace, int32_t batch, int32_t t_max);
+TPLB_API size_t tplb_workspace_bytes(int32_t batch, int32_t scenes, int32_t t_max);
 /* Device address of the [8][B] candidate costs of the last line search. */
-TPLB_API void* tplb_workspace_cand_cost(void* workspace, int32_t batch, int32_t t_max);
+TPLB_API void* tplb_workspace_cand_cost(void* workspace, int32_t batch, int32_t scenes, int32_t t_max);
+
+/* Device address of the [3][B] int32 work counters of the last update(): linearisations,
+ * backward sweeps and the rollouts a sequential line search would have executed
+ * (accepted index + 1, or 8 on failure; + 1 for the initial rollout).  They feed the
+ * algorithmic-flop count of the roofline. */
+TPLB_API void* tplb_workspace_counters(void* workspace, int32_t batch, int32_t scenes, int32_t t_max);
 
 /* One `update()` for every problem of the batch (optim.c:1091-1160): initial rollout
  * and cost, then max_lg_iterations x { multiplier update; up to max_iterations x
@@ -153,9 +166,32 @@ TPLB_API void* tplb_workspace_cand_cost(void* workspace, int32_t batch, int32_t 
  * search; regularisation schedule; relative-change stop } }, termination flags. */
 TPLB_API int32_t tplb_update(const tplb_batch* batch, void* stream);
 
-/* Derivative blocks of the CURRENT trajectory into workspace.deriv (optim.c:896-912),
- * for every problem regardless of solver state. */
+/* Same launches as tplb_update() with a CUDA-event pair around every launch, so the
+ * time spent in each kernel class and the launch counts can be attributed (measurement
+ * aid: it synchronises after every launch).  Either output may be NULL. */
+enum {
+    TPLB_K_STAGE_CONSTS = 0,  /* stage_constants_kernel                                   */
+    TPLB_K_ROLLOUT_INIT = 1,  /* rollout_kernel<init> + stage_cost_kernel + init_cost_kernel */
+    TPLB_K_MULTIPLIER = 2,    /* multiplier_kernel                                         */
+    TPLB_K_LINEARIZE = 3,     /* linearize_kernel                                          */
+    TPLB_K_BACKWARD = 4,      /* backward_kernel                                           */
+    TPLB_K_ROLLOUT = 5,       /* rollout_kernel<line search>: 8 step sizes                 */
+    TPLB_K_STAGE_COST = 6,    /* stage_cost_kernel on the 8 candidates                     */
+    TPLB_K_SELECT = 7,        /* select_kernel                                             */
+    TPLB_K_ACCEPT = 8,        /* accept_kernel                                             */
+    TPLB_K_FINALIZE = 9,      /* finalize_kernel                                           */
+    TPLB_NUM_KERNEL_CLASSES = 10
+};
+TPLB_API int32_t tplb_update_profiled(const tplb_batch* batch, void* stream,
+                                      float* ms_by_class, int32_t* launches_by_class);
+
+/* Derivative records of the CURRENT trajectory (optim.c:896-912) for every problem
+ * regardless of solver state, expanded into batch->deriv_dense. */
 TPLB_API int32_t tplb_linearize(const tplb_batch* batch, void* stream);
+
+/* Expand the records the last update() linearised (what the reference's fx..lux getters
+ * show after update(), optim.c:1663-1669) into batch->deriv_dense. */
+TPLB_API int32_t tplb_expand_derivatives(const tplb_batch* batch, void* stream);
 
 /* Warm-start shift by `amount` stages for all problems, or by amounts[b] when
  * `amounts` (device, [B]) is not NULL (optim.c:1162-1177). */

@@ -31,3 +31,12 @@ print("ms per update:", [f"{t:.3f}" for t in times])
 best = min(times)
 print(f"{a.model} B={a.batch} N={a.horizon} it={a.iters}: {best:.3f} ms -> {a.batch/best*1e3:.3e} solves/s")
 print("iterations", q0.iterations[:8].tolist(), "cost", q0.traj_costs[:4].tolist())
+q0._x.copy_(x0); q0._u.copy_(u0)
+for k, v in st.items(): q0._status[k].copy_(v)
+prof = q0.update_profiled()
+tot = sum(ms for ms, _ in prof.values())
+print("profiled (sync after every launch): total %.3f ms" % tot)
+for k, (ms, n) in prof.items():
+    print(f"  {k:14s} {ms:8.3f} ms  {n:3d} launches  {ms/max(n,1)*1e3:8.1f} us/launch  {ms/tot:6.1%}")
+lin, bwd, roll = q0.work_counters()
+print("work per solve: lin %.2f bwd %.2f rollouts %.2f" % (lin.float().mean(), bwd.float().mean(), roll.float().mean()))

@@ -22,6 +22,7 @@ class ModelInfo(C.Structure):
         ("deriv_stride", C.c_int32),
         ("off_fx", C.c_int32), ("off_fu", C.c_int32), ("off_lx", C.c_int32), ("off_lu", C.c_int32),
         ("off_lxx", C.c_int32), ("off_luu", C.c_int32), ("off_lux", C.c_int32),
+        ("deriv_compact", C.c_int32), ("num_stage_consts", C.c_int32),
     ]
 
 
@@ -42,13 +43,15 @@ class Batch(C.Structure):
         ("scene_index", _D), ("scalars", _D),
         ("arrays", _D * MAX_ARRAYS), ("array_len", C.c_int32 * MAX_ARRAYS),
         ("workspace", _D), ("workspace_bytes", C.c_size_t),
+        ("deriv_dense", _D),
     ]
 
 
 #: every symbol include/tplb200.h declares (tests check the library exports all of them)
 EXPORTS = (
     "tplb_abi_version", "tplb_model", "tplb_last_error", "tplb_workspace_bytes",
-    "tplb_workspace_deriv", "tplb_workspace_cand_cost", "tplb_update", "tplb_linearize",
+    "tplb_workspace_cand_cost", "tplb_workspace_counters",
+    "tplb_update", "tplb_update_profiled", "tplb_linearize", "tplb_expand_derivatives",
     "tplb_shift", "tplb_dynamics", "tplb_argmin_groups", "tplb_measure_fp64_tflops",
 )
 
@@ -65,12 +68,14 @@ def load(path):
     lib.tplb_model.restype = C.POINTER(ModelInfo)
     lib.tplb_last_error.restype = C.c_char_p
     lib.tplb_workspace_bytes.restype = C.c_size_t
-    lib.tplb_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
-    lib.tplb_workspace_deriv.restype = C.c_void_p
-    lib.tplb_workspace_deriv.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    lib.tplb_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     lib.tplb_workspace_cand_cost.restype = C.c_void_p
-    lib.tplb_workspace_cand_cost.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
-    for fn in ("tplb_update", "tplb_linearize"):
+    lib.tplb_workspace_cand_cost.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+    lib.tplb_workspace_counters.restype = C.c_void_p
+    lib.tplb_workspace_counters.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+    lib.tplb_update_profiled.restype = C.c_int32
+    lib.tplb_update_profiled.argtypes = [C.POINTER(Batch), C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    for fn in ("tplb_update", "tplb_linearize", "tplb_expand_derivatives"):
         getattr(lib, fn).restype = C.c_int32
         getattr(lib, fn).argtypes = [C.POINTER(Batch), C.c_void_p]
     lib.tplb_shift.restype = C.c_int32
@@ -99,10 +104,14 @@ def model_info(lib):
         state_names=strs(m.state_names, m.X), action_names=strs(m.action_names, m.U),
         scalar_names=strs(m.scalar_names, m.num_scalars), array_names=strs(m.array_names, m.num_arrays),
         param_order=strs(m.param_order, m.num_params),
-        deriv_stride=m.deriv_stride,
+        deriv_stride=m.deriv_stride, deriv_compact=m.deriv_compact, num_stage_consts=m.num_stage_consts,
         offsets=dict(fx=m.off_fx, fu=m.off_fu, lx=m.off_lx, lu=m.off_lu,
                      lxx=m.off_lxx, luu=m.off_luu, lux=m.off_lux),
     )
+
+
+KERNEL_CLASSES = ("stage_consts", "rollout_init", "multiplier", "linearize", "backward",
+                  "rollout", "stage_cost", "select", "accept", "finalize")
 
 
 def check(lib, code, what):

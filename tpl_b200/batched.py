@@ -174,6 +174,8 @@ class BatchedOptim:
         self._scalars = z(max(1, len(self._scalar_index)), S, **f64)
         self._arrays = [z(S, 0, **f64) for _ in self._array_index]
         self._workspace = None
+        self._deriv_dense = None
+        self._deriv_stale = True
         self._dirty = True
         self._events = None
 
@@ -242,10 +244,21 @@ class BatchedOptim:
         return v
 
     def _deriv_view(self, name, comp_shape):
-        self._ensure_workspace()
+        """fx..lux: the solver keeps only the entries that are not identically 0/1;
+        the dense records the reference exposes are expanded on demand."""
+        if self._deriv_dense is None:
+            self._deriv_dense = torch.zeros(self.t_max, self._info["deriv_stride"], self.batch,
+                                            dtype=torch.float64, device=self.device)
+            self._deriv_stale = True
+        if self._deriv_stale and self.device.type == "cuda":
+            with torch.cuda.device(self.device):
+                q = self._descriptor()
+                _cabi.check(self._lib, self._lib.tplb_expand_derivatives(C.byref(q), self._stream()),
+                            "tplb_expand_derivatives")
+            self._deriv_stale = False
         off = self._info["offsets"][name]
         n = int(np.prod(comp_shape))
-        blk = self._deriv[:self._T, off:off + n, :]
+        blk = self._deriv_dense[:self._T, off:off + n, :]
         return self._traj_view(blk, self._T, comp_shape)
 
     def __getattr__(self, n):
@@ -327,17 +340,9 @@ class BatchedOptim:
     # -- C ABI plumbing ---------------------------------------------------------------
     def _ensure_workspace(self):
         if self._workspace is None:
-            nbytes = self._lib.tplb_workspace_bytes(self.batch, self.t_max)
+            nbytes = self._lib.tplb_workspace_bytes(self.batch, self.scenes, self.t_max)
             self._workspace = torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
             self._workspace_bytes = nbytes
-            stride = self._info["deriv_stride"]
-            n = self.t_max * stride * self.batch
-            if self.device.type == "cuda":
-                base = self._lib.tplb_workspace_deriv(self._workspace.data_ptr(), self.batch, self.t_max)
-                off = (base - self._workspace.data_ptr()) // 8
-            else:
-                off = 0
-            self._deriv = self._workspace[off:off + n].view(self.t_max, stride, self.batch)
 
     def _descriptor(self):
         self._ensure_workspace()
@@ -365,6 +370,7 @@ class BatchedOptim:
             q.array_len[i] = a.shape[1]
         q.workspace = self._workspace.data_ptr()
         q.workspace_bytes = self._workspace_bytes
+        q.deriv_dense = self._deriv_dense.data_ptr() if self._deriv_dense is not None else None
         return q
 
     def _require_cuda(self, what):
@@ -386,13 +392,42 @@ class BatchedOptim:
             _cabi.check(self._lib, self._lib.tplb_update(C.byref(q), self._stream()), "tplb_update")
             e1.record()
             self._events = (e0, e1)
+            self._deriv_stale = True
+
+    def update_profiled(self):
+        """``update()`` with a CUDA-event pair around every kernel launch: returns
+        ``{kernel class: (milliseconds, launches)}``.  Measurement aid (synchronises
+        after each launch); results are identical to ``update()``."""
+        self._require_cuda("update_profiled()")
+        n = len(_cabi.KERNEL_CLASSES)
+        ms, cnt = (C.c_float * n)(), (C.c_int32 * n)()
+        with torch.cuda.device(self.device):
+            q = self._descriptor()
+            _cabi.check(self._lib, self._lib.tplb_update_profiled(C.byref(q), self._stream(), ms, cnt),
+                        "tplb_update_profiled")
+            self._deriv_stale = True
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(_cabi.KERNEL_CLASSES)}
+
+    def work_counters(self):
+        """(linearisations, backward sweeps, sequential-equivalent rollouts) of the
+        last ``update()``, each a (B,) int32 device tensor."""
+        self._require_cuda("work_counters()")
+        self._ensure_workspace()
+        base = self._lib.tplb_workspace_counters(self._workspace.data_ptr(), self.batch, self.scenes, self.t_max)
+        off = (base - self._workspace.data_ptr()) // 4
+        c = self._workspace.view(torch.int32)[off:off + 3 * self.batch].view(3, self.batch)
+        return c[0], c[1], c[2]
 
     def linearize(self):
         """Fill ``fx, fu, lx, lu, lxx, luu, lux`` for the current trajectory."""
         self._require_cuda("linearize()")
+        if self._deriv_dense is None:
+            self._deriv_dense = torch.zeros(self.t_max, self._info["deriv_stride"], self.batch,
+                                            dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
             q = self._descriptor()
             _cabi.check(self._lib, self._lib.tplb_linearize(C.byref(q), self._stream()), "tplb_linearize")
+        self._deriv_stale = False
 
     def shift(self, amount):
         """Warm-start shift; ``amount`` is an int or a (B,) integer array."""
@@ -481,6 +516,9 @@ class BatchedOptim:
         if self._workspace is not None:
             o._ensure_workspace()
             o._workspace.copy_(self._workspace)
+        if self._deriv_dense is not None:
+            o._deriv_dense = self._deriv_dense.clone()
+            o._deriv_stale = self._deriv_stale
         return o
 
     def __getstate__(self):

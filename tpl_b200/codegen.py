@@ -158,6 +158,23 @@ def _one_line(text):
     return re.sub(r"\s*\n\s*", " ", text)
 
 
+def _pair_sincos(exprs):
+    """sin(a) and cos(a) of the same argument -> one ``sincos`` call.  Returns the
+    rewritten expressions and the list of paired arguments (already rewritten)."""
+    sins, coss = {}, {}
+    for e in exprs:
+        for f in e.atoms(sp.sin):
+            sins[f.args[0]] = f
+        for f in e.atoms(sp.cos):
+            coss[f.args[0]] = f
+    args = sorted((a for a in sins if a in coss), key=str)
+    repl = {}
+    for k, a in enumerate(args):
+        repl[sins[a]] = sp.Symbol(f"sn{k}")
+        repl[coss[a]] = sp.Symbol(f"cs{k}")
+    return [e.xreplace(repl) for e in exprs], [a.xreplace(repl) for a in args]
+
+
 def print_body(printer: ModelPrinter, outputs: Sequence[Tuple[str, sp.MatrixBase]],
                indent="    ") -> str:
     """One CSE pass over all ``outputs`` and the statements that evaluate them."""
@@ -168,14 +185,42 @@ def print_body(printer: ModelPrinter, outputs: Sequence[Tuple[str, sp.MatrixBase
         spans.append((name, len(flat), len(es)))
         flat.extend(es)
     printer.used_scalars = set()
+    pair_args = []
+    if printer.dialect.name == "cuda":
+        flat, pair_args = _pair_sincos(flat)
+    n_out = len(flat)
     if flat:
-        common, reduced = sp.cse(flat, symbols=sp.numbered_symbols("v"))
+        common, reduced = sp.cse(flat + pair_args, symbols=sp.numbered_symbols("v"))
     else:
         common, reduced = [], []
-    lines = []
+
+    # definitions in dependency order: CSE temporaries and sincos pairs
+    defs = {}
     for sym, expr in common:
         ctype = "bool" if _is_boolean(expr) else real
-        lines.append(f"{indent}const {ctype} {sym} = {_one_line(printer.doprint(expr))};")
+        defs[sym.name] = ([sym.name], {f.name for f in expr.free_symbols},
+                          f"{indent}const {ctype} {sym} = {_one_line(printer.doprint(expr))};")
+    for k in range(len(pair_args)):
+        arg = reduced[n_out + k]
+        node = ([f"sn{k}", f"cs{k}"], {f.name for f in arg.free_symbols},
+                f"{indent}{real} sn{k}, cs{k}; sincos({_one_line(printer.doprint(arg))}, &sn{k}, &cs{k});")
+        defs[f"sn{k}"] = defs[f"cs{k}"] = node
+    lines, done = [], set()
+
+    def need(name):
+        if name in done or name not in defs:
+            return
+        produced, deps, text = defs[name]
+        done.update(produced)
+        for dep in sorted(deps):
+            need(dep)
+        lines.append(text)
+
+    for sym, _ in common:
+        need(sym.name)
+    for e in reduced[:n_out]:
+        for f in sorted(e.free_symbols, key=str):
+            need(f.name)
     for name, start, n in spans:
         for k in range(n):
             lines.append(f"{indent}{name}[{k}] = {_one_line(printer.doprint(reduced[start + k]))};")
@@ -188,9 +233,14 @@ def print_body(printer: ModelPrinter, outputs: Sequence[Tuple[str, sp.MatrixBase
 # CUDA model header
 # ---------------------------------------------------------------------------------
 
-_STAGE_ARGS = "const R* x, const R* u, const R* lg_mult, const R* lg_weight, const R t, const R dt"
-_DYN_ARGS = "const R* x, const R* u, const R t, const R dt"
-_END_ARGS = "const R* x, const R t, const R dt"
+_STAGE_ARGS = ("const R* x, const R* u, const R* lg_mult, const R* lg_weight, const R* sc, "
+               "const R t, const R dt")
+_DYN_ARGS = "const R* x, const R* u, const R* sc, const R t, const R dt"
+_END_ARGS = "const R* x, const R* sc, const R t, const R dt"
+
+# order of the blocks inside one stage's derivative record
+DERIV_BLOCKS = ("stateJacobian", "actionJacobian", "stateGradient", "actionGradient",
+                "stateStateHessian", "actionActionHessian", "actionStateHessian")
 
 
 def _cuda_fn(name, args, outs, body):
@@ -201,29 +251,79 @@ def _cuda_fn(name, args, outs, body):
             f"    }}\n")
 
 
-def _c_array(ctype, name, values, fmt="%d"):
-    vals = ", ".join(fmt % v for v in values) if values else "0"
+def _lookup_fn(name, values, ctype="int"):
+    """``constexpr`` table lookup usable from host and device code."""
+    vals = ", ".join(str(v) for v in values) if values else "0"
     n = max(1, len(values))
-    return f"    static constexpr {ctype} {name}[{n}] = {{{vals}}};\n"
+    return (f"    __host__ __device__ static constexpr {ctype} {name}(int e) {{\n"
+            f"        constexpr {ctype} table[{n}] = {{{vals}}};\n"
+            f"        return table[e];\n"
+            f"    }}\n")
+
+
+def hoist_stage_constants(d: Derivation):
+    """Interpolation lookups whose arguments depend only on the stage index, the
+    step and the parameters are constant per (scene, stage) for a whole solve
+    (SURVEY.md appendix C).  Returns the routines with every such call replaced
+    by ``sc[i]`` and the list of hoisted calls; the values are produced by the
+    same printed expression, so nothing changes numerically."""
+    allowed = {"t", "dt"} | set(d.scalar_params) | set(d.array_params)
+    calls = set()
+    for m in d.routines.values():
+        for fn in spx.OPAQUE_FUNCTIONS:
+            for call in m.atoms(fn):
+                if all(s.name in allowed for s in call.free_symbols):
+                    calls.add(call)
+    calls = sorted(calls, key=str)
+    repl = {c: sp.Symbol(f"sc[{i}]") for i, c in enumerate(calls)}
+    routines = {n: (m.xreplace(repl) if m.shape[0] * m.shape[1] else m) for n, m in d.routines.items()}
+    return routines, calls
+
+
+def derivative_layout(r):
+    """Compact storage of one stage's derivative record.
+
+    Dense order: fx | fu | lx | lu | lxx | luu | lux, row-major each.  Entries that
+    are identically 0 or 1 are not stored (slot -1 / -2); the two halves of the
+    symmetric Hessian blocks share one slot.  Returns (slot per dense entry,
+    owner flag per dense entry, number of slots, dense offsets)."""
+    slots, owner, offsets = [], [], {}
+    n = 0
+    for name in DERIV_BLOCKS:
+        m = r[name]
+        offsets[name] = len(slots)
+        rows, cols = m.shape
+        local = {}
+        for i in range(rows):
+            for j in range(cols):
+                e = m[i, j]
+                if e == 0:
+                    slots.append(-1); owner.append(0)
+                elif e == 1:
+                    slots.append(-2); owner.append(0)
+                elif name in ("stateStateHessian", "actionActionHessian") and j < i and m[j, i] == e:
+                    slots.append(local[(j, i)]); owner.append(0)
+                else:
+                    local[(i, j)] = n
+                    slots.append(n); owner.append(1)
+                    n += 1
+    return slots, owner, n, offsets
 
 
 def emit_cuda_model(d: Derivation, name: str, definition_hash: str) -> str:
     """The ``struct Model`` consumed by csrc/solver.cuh."""
-    r = d.routines
+    r, hoisted = hoist_stage_constants(d)
     pr = ModelPrinter(d, CUDA)
     ind = "        "
     parts = []
+    parts.append(_cuda_fn("stage_constants", "const R t, const R dt", ["sc"],
+                          print_body(pr, [("sc", sp.Matrix(hoisted) if hoisted else sp.zeros(0, 1))], ind)))
     parts.append(_cuda_fn("ct_dynamics", _DYN_ARGS, ["f"],
                           print_body(pr, [("f", r["ctDynamics"])], ind)))
     parts.append(_cuda_fn("dynamics_jacobians", _DYN_ARGS, ["fx", "fu"],
                           print_body(pr, [("fx", r["stateJacobian"]), ("fu", r["actionJacobian"])], ind)))
     parts.append(_cuda_fn("stage_cost", _STAGE_ARGS, ["c"],
                           print_body(pr, [("c", r["costs"])], ind)))
-    parts.append(_cuda_fn("cost_derivatives", _STAGE_ARGS, ["lx", "lu", "lxx", "luu", "lux"],
-                          print_body(pr, [("lx", r["stateGradient"]), ("lu", r["actionGradient"]),
-                                          ("lxx", r["stateStateHessian"]),
-                                          ("luu", r["actionActionHessian"]),
-                                          ("lux", r["actionStateHessian"])], ind)))
     parts.append(_cuda_fn("cost_gradients", _STAGE_ARGS, ["lx", "lu"],
                           print_body(pr, [("lx", r["stateGradient"]), ("lu", r["actionGradient"])], ind)))
     parts.append(_cuda_fn("linearize", _STAGE_ARGS, ["fx", "fu", "lx", "lu", "lxx", "luu", "lux"],
@@ -243,6 +343,10 @@ def emit_cuda_model(d: Derivation, name: str, definition_hash: str) -> str:
         body = ", ".join(f'"{s}"' for s in items) if items else '""'
         return f"    static constexpr const char* {tag}[{max(1, len(items))}] = {{{body}}};\n"
 
+    slots, owner, nslots, offsets = derivative_layout(r)
+    vxx_kind = entry_kinds(r["endHessian"])
+    hoisted_doc = "".join(f"    //   sc[{i}] = {c}\n" for i, c in enumerate(hoisted))
+
     head = (
         f"// AUTO-GENERATED by tpl_b200.codegen from the problem definition '{name}'.\n"
         f"// definition sha1: {definition_hash}\n"
@@ -254,6 +358,7 @@ def emit_cuda_model(d: Derivation, name: str, definition_hash: str) -> str:
         f"    static constexpr int C = {d.C};\n"
         f"    static constexpr int NUM_SCALARS = {len(d.scalar_params)};\n"
         f"    static constexpr int NUM_ARRAYS = {len(d.array_params)};\n"
+        f"    static constexpr int NUM_PARAMS = {len(d.param_order)};\n"
         f'    static constexpr const char* NAME = "{name}";\n'
         f'    static constexpr const char* DEFINITION_SHA1 = "{definition_hash}";\n'
         + names("STATE_NAMES", d.state_names)
@@ -261,14 +366,17 @@ def emit_cuda_model(d: Derivation, name: str, definition_hash: str) -> str:
         + names("SCALAR_NAMES", d.scalar_params)
         + names("ARRAY_NAMES", d.array_params)
         + names("PARAM_ORDER", d.param_order)
-        + f"    static constexpr int NUM_PARAMS = {len(d.param_order)};\n"
-        + "    // structure of the derivative blocks: 0 = zero, 1 = one, 2 = general\n"
-        + _c_array("signed char", "FX_KIND", entry_kinds(r["stateJacobian"]))
-        + _c_array("signed char", "FU_KIND", entry_kinds(r["actionJacobian"]))
-        + _c_array("signed char", "LXX_KIND", entry_kinds(r["stateStateHessian"]))
-        + _c_array("signed char", "LUU_KIND", entry_kinds(r["actionActionHessian"]))
-        + _c_array("signed char", "LUX_KIND", entry_kinds(r["actionStateHessian"]))
-        + _c_array("signed char", "VXX_END_KIND", entry_kinds(r["endHessian"]))
+        + "\n    // per-(scene, stage) constants: lookups that depend on the stage index only\n"
+        + hoisted_doc
+        + f"    static constexpr int NUM_STAGE_CONSTS = {len(hoisted)};\n"
+        + "\n    // one stage's derivative record: dense order fx|fu|lx|lu|lxx|luu|lux (row-major);\n"
+        + "    // deriv_slot(e) >= 0: index in the compact record, -1: identically 0, -2: identically 1\n"
+        + f"    static constexpr int DERIV_DENSE = {len(slots)};\n"
+        + f"    static constexpr int DERIV_COMPACT = {nslots};\n"
+        + _lookup_fn("deriv_slot", slots)
+        + _lookup_fn("deriv_owner", owner)
+        + "    // end-cost Hessian: 0 = zero, 1 = one, 2 = general\n"
+        + _lookup_fn("vxx_end_kind", vxx_kind)
         + "\n"
     )
     return head + "\n".join(parts) + "};\n"

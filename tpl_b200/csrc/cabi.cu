@@ -47,6 +47,8 @@ int validate(const tplb_batch* q) {
     if (q->t_max > TPLB_HORIZON_MAX || q->horizon < 1 || q->horizon > q->t_max)
         return fail(TPLB_E_HORIZON, "horizon must satisfy 1 <= horizon <= t_max <= 299");
     if (q->opt_start != 0) return fail(TPLB_E_UNSUPPORTED, "opt_start != 0 is not supported");
+    if (q->integrator_type < TPLB_EULER || q->integrator_type > TPLB_RK4)
+        return fail(TPLB_E_UNSUPPORTED, "integrator_type must be EULER, HEUN or RK4");
     if (!q->x || !q->u || !q->k || !q->K || !q->u_min || !q->u_max || !q->traj_costs || !q->alpha ||
         !q->mu || !q->iterations || !q->lg_iterations || !q->mu_step || !q->trajectory_changed ||
         !q->improved || !q->termination_condition || !q->scene_index || !q->workspace)
@@ -58,7 +60,7 @@ int validate(const tplb_batch* q) {
         if (q->array_len[a] > 0 && !q->arrays[a]) return fail(TPLB_E_ARG, "a parameter array is NULL");
     if (q->keep_previous && (!q->prev_x || !q->prev_k)) return fail(TPLB_E_ARG, "prev_x/prev_k are NULL");
     size_t need = 0;
-    tplb::carve<Model>(nullptr, q->batch, q->t_max, &need);
+    tplb::carve<Model>(nullptr, q->batch, q->scenes, q->t_max, &need);
     if (q->workspace_bytes < need) return fail(TPLB_E_ARG, "workspace too small");
     return 0;
 }
@@ -82,64 +84,177 @@ const tplb_model_info* tplb_model(void) {
         Model::NAME, Model::DEFINITION_SHA1,
         names(Model::STATE_NAMES), names(Model::ACTION_NAMES), names(Model::SCALAR_NAMES),
         names(Model::ARRAY_NAMES), names(Model::PARAM_ORDER),
-        Dm::STRIDE, Dm::OFF_FX, Dm::OFF_FU, Dm::OFF_LX, Dm::OFF_LU, Dm::OFF_LXX, Dm::OFF_LUU, Dm::OFF_LUX,
+        Dm::DENSE, Dm::OFF_FX, Dm::OFF_FU, Dm::OFF_LX, Dm::OFF_LU, Dm::OFF_LXX, Dm::OFF_LUU, Dm::OFF_LUX,
+        Model::DERIV_COMPACT, Model::NUM_STAGE_CONSTS,
     };
     return &info;
 }
 
 const char* tplb_last_error(void) { return g_error; }
 
-size_t tplb_workspace_bytes(int32_t batch, int32_t t_max) {
+size_t tplb_workspace_bytes(int32_t batch, int32_t scenes, int32_t t_max) {
     size_t need = 0;
-    tplb::carve<Model>(nullptr, batch, t_max, &need);
+    tplb::carve<Model>(nullptr, batch, scenes, t_max, &need);
     return need;
 }
 
-void* tplb_workspace_deriv(void* workspace, int32_t batch, int32_t t_max) {
-    return tplb::carve<Model>(workspace, batch, t_max).deriv;
+void* tplb_workspace_cand_cost(void* workspace, int32_t batch, int32_t scenes, int32_t t_max) {
+    return tplb::carve<Model>(workspace, batch, scenes, t_max).cand_cost;
 }
 
-void* tplb_workspace_cand_cost(void* workspace, int32_t batch, int32_t t_max) {
-    return tplb::carve<Model>(workspace, batch, t_max).cand_cost;
+void* tplb_workspace_counters(void* workspace, int32_t batch, int32_t scenes, int32_t t_max) {
+    return tplb::carve<Model>(workspace, batch, scenes, t_max).counters;
 }
+
+}  // extern "C"
+
+namespace {
+
+// Per-kernel-class timing for tplb_update_profiled(): CUDA events between launches.
+struct Profiler {
+    cudaStream_t st;
+    bool on;
+    cudaEvent_t ev[2];
+    float ms[TPLB_NUM_KERNEL_CLASSES];
+    int launches[TPLB_NUM_KERNEL_CLASSES];
+    explicit Profiler(cudaStream_t s, bool enable) : st(s), on(enable) {
+        std::memset(ms, 0, sizeof ms);
+        std::memset(launches, 0, sizeof launches);
+        if (on) { cudaEventCreate(&ev[0]); cudaEventCreate(&ev[1]); }
+    }
+    ~Profiler() { if (on) { cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]); } }
+    void before() { if (on) cudaEventRecord(ev[0], st); }
+    void after(int cls) {
+        launches[cls] += (cls == TPLB_K_ROLLOUT_INIT) ? 3 : 1;
+        if (!on) return;
+        cudaEventRecord(ev[1], st);
+        cudaEventSynchronize(ev[1]);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ev[0], ev[1]);
+        ms[cls] += t;
+    }
+};
+
+int run_update(const tplb_batch* qp, void* stream_, Profiler& prof);
+
+}  // namespace
+
+extern "C" {
 
 int32_t tplb_update(const tplb_batch* qp, void* stream_) {
+    Profiler prof(static_cast<cudaStream_t>(stream_), false);
+    return run_update(qp, stream_, prof);
+}
+
+int32_t tplb_update_profiled(const tplb_batch* qp, void* stream_, float* ms_by_class, int32_t* launches_by_class) {
+    Profiler prof(static_cast<cudaStream_t>(stream_), true);
+    const int rc = run_update(qp, stream_, prof);
+    for (int i = 0; i < TPLB_NUM_KERNEL_CLASSES; ++i) {
+        if (ms_by_class) ms_by_class[i] = prof.ms[i];
+        if (launches_by_class) launches_by_class[i] = prof.launches[i];
+    }
+    return rc;
+}
+
+}  // extern "C"
+
+namespace {
+
+constexpr int PB = 32;                                     // problems per rollout / select block
+
+template <bool kInit>
+void launch_rollout(const tplb_batch& q, const tplb::Workspace& ws, cudaStream_t st) {
+    const dim3 grid((q.batch + PB - 1) / PB), block(PB, kInit ? 1 : tplb::kAlphas);
+    switch (q.integrator_type) {
+        case TPLB_EULER: tplb::rollout_kernel<Model, PB, kInit, TPLB_EULER><<<grid, block, 0, st>>>(q, ws); break;
+        case TPLB_HEUN: tplb::rollout_kernel<Model, PB, kInit, TPLB_HEUN><<<grid, block, 0, st>>>(q, ws); break;
+        default: tplb::rollout_kernel<Model, PB, kInit, TPLB_RK4><<<grid, block, 0, st>>>(q, ws); break;
+    }
+}
+
+int run_update(const tplb_batch* qp, void* stream_, Profiler& prof) {
     if (int e = validate(qp)) return e;
     const tplb_batch q = *qp;
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
-    const tplb::Workspace ws = tplb::carve<Model>(q.workspace, q.batch, q.t_max);
-    const int B = q.batch, T = q.horizon;
+    const tplb::Workspace ws = tplb::carve<Model>(q.workspace, q.batch, q.scenes, q.t_max);
+    const int B = q.batch, T = q.horizon, S = q.scenes;
     const int pb = problem_block(B);
     const dim3 pgrid((B + pb - 1) / pb);
     const int sb = 128;                                    // stage-parallel kernels
-    const dim3 sgrid((B + sb - 1) / sb, T);
-    constexpr int PB = 32;                                 // problems per line-search block
+    const unsigned sgx = (B + sb - 1) / sb;
+    const size_t cx_stride = (size_t)(q.t_max + 1) * Model::X * B;
+    const size_t cu_stride = (size_t)q.t_max * Model::U * B;
 
-    tplb::rollout_init_kernel<Model><<<pgrid, pb, 0, st>>>(q);
+    prof.before();
+    tplb::stage_constants_kernel<Model><<<dim3((S + sb - 1) / sb, T + 1), sb, 0, st>>>(q, ws);
+    prof.after(TPLB_K_STAGE_CONSTS);
+
+    prof.before();
+    launch_rollout<true>(q, ws, st);
+    tplb::stage_cost_kernel<Model><<<dim3(sgx, T + 1, 1), sb, 0, st>>>(q, ws, q.x, q.u, 0, 0, 0);
+    tplb::init_cost_kernel<<<(B + sb - 1) / sb, sb, 0, st>>>(q, ws);
+    prof.after(TPLB_K_ROLLOUT_INIT);
 
     int lg = 0;
     for (; lg < q.max_lg_iterations; ++lg) {
-        tplb::multiplier_kernel<Model><<<dim3(sgrid.x, Model::C > 0 ? T : 1), sb, 0, st>>>(q, ws);
+        prof.before();
+        tplb::multiplier_kernel<Model><<<dim3(sgx, Model::C > 0 ? T : 1), sb, 0, st>>>(q, ws);
+        prof.after(TPLB_K_MULTIPLIER);
         for (int s = 0; s < q.max_iterations; ++s) {
-            tplb::linearize_kernel<Model, false><<<sgrid, sb, 0, st>>>(q, ws);
+            prof.before();
+            tplb::linearize_kernel<Model, false><<<dim3(sgx, T), sb, 0, st>>>(q, ws);
+            prof.after(TPLB_K_LINEARIZE);
+            prof.before();
             if (q.use_quadratic_terms)
                 tplb::backward_kernel<Model><<<pgrid, pb, 0, st>>>(q, ws, s);
             else
                 tplb::backward_first_order_kernel<Model><<<pgrid, pb, 0, st>>>(q, ws, s);
-            tplb::line_search_kernel<Model, PB><<<(B + PB - 1) / PB, dim3(PB, tplb::kAlphas), 0, st>>>(q, ws);
-            tplb::accept_kernel<Model><<<dim3(sgrid.x, T + 1), sb, 0, st>>>(q, ws);
+            prof.after(TPLB_K_BACKWARD);
+            prof.before();
+            launch_rollout<false>(q, ws, st);
+            prof.after(TPLB_K_ROLLOUT);
+            prof.before();
+            tplb::stage_cost_kernel<Model><<<dim3(sgx, T + 1, tplb::kAlphas), sb, 0, st>>>(
+                q, ws, ws.cand_x, ws.cand_u, cx_stride, cu_stride, 1);
+            prof.after(TPLB_K_STAGE_COST);
+            prof.before();
+            tplb::select_kernel<PB><<<(B + PB - 1) / PB, dim3(PB, tplb::kAlphas), 0, st>>>(q, ws);
+            prof.after(TPLB_K_SELECT);
+            prof.before();
+            tplb::accept_kernel<Model><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
+            prof.after(TPLB_K_ACCEPT);
         }
     }
+    prof.before();
     tplb::finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(q, lg);
+    prof.after(TPLB_K_FINALIZE);
     return check_launch("tplb_update");
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t tplb_expand_derivatives(const tplb_batch* qp, void* stream_) {
+    if (int e = validate(qp)) return e;
+    if (!qp->deriv_dense) return fail(TPLB_E_ARG, "deriv_dense is NULL");
+    const tplb_batch q = *qp;
+    const tplb::Workspace ws = tplb::carve<Model>(q.workspace, q.batch, q.scenes, q.t_max);
+    const dim3 grid((q.batch + 127) / 128, q.horizon);
+    tplb::expand_derivatives_kernel<Model><<<grid, 128, 0, static_cast<cudaStream_t>(stream_)>>>(q, ws, q.deriv_dense);
+    return check_launch("tplb_expand_derivatives");
 }
 
 int32_t tplb_linearize(const tplb_batch* qp, void* stream_) {
     if (int e = validate(qp)) return e;
+    if (!qp->deriv_dense) return fail(TPLB_E_ARG, "deriv_dense is NULL");
     const tplb_batch q = *qp;
-    const tplb::Workspace ws = tplb::carve<Model>(q.workspace, q.batch, q.t_max);
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    const tplb::Workspace ws = tplb::carve<Model>(q.workspace, q.batch, q.scenes, q.t_max);
     const dim3 grid((q.batch + 127) / 128, q.horizon);
-    tplb::linearize_kernel<Model, true><<<grid, 128, 0, static_cast<cudaStream_t>(stream_)>>>(q, ws);
+    tplb::stage_constants_kernel<Model><<<dim3((q.scenes + 127) / 128, q.horizon + 1), 128, 0, st>>>(q, ws);
+    tplb::linearize_kernel<Model, true><<<grid, 128, 0, st>>>(q, ws);
+    tplb::expand_derivatives_kernel<Model><<<grid, 128, 0, st>>>(q, ws, q.deriv_dense);
     return check_launch("tplb_linearize");
 }
 

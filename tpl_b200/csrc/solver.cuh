@@ -1,18 +1,31 @@
 // Batched iLQR kernels for sm_100a.  One instantiation per generated `Model`.
 //
 // Restates, for B independent problems, the solver of
-// /root/reference/library/tpl/optim/templates/optim.c ("optim.c") :
-//   rollout_init_kernel   optim.c:1096-1111   initial rollout + trajectory cost
-//   multiplier_kernel     optim.c:1115-1136   multiplier update, per-outer-iteration reset
-//   linearize_kernel      optim.c:896-912     derivative blocks of every stage   [stage parallel]
-//   backward_kernel       optim.c:914-985     Riccati sweep + gains + box limits [problem parallel]
-//   line_search_kernel    optim.c:732-792, 840-873, 987-1006   8 step sizes at once, first
-//                                             improving one wins; mu schedule; stop test
-//   accept_kernel         optim.c:844-848     copy the winning candidate        [stage parallel]
-//   finalize_kernel       optim.c:1145-1149   termination flag
+// /root/reference/library/tpl/optim/templates/optim.c ("optim.c"):
+//
+//   stage_constants_kernel  per-(scene, stage) interpolation lookups, once per update()
+//   rollout_kernel<Init>    optim.c:1096-1107    x[t+1] = F(x[t], u[t])            [problem parallel]
+//   rollout_kernel<Search>  optim.c:732-775      8 step sizes alpha_i = 10^-i at once:
+//                                                u' = clip(u + alpha k + K (x' - x)), x' = F(x', u')
+//   stage_cost_kernel       optim.c:776-789, 1105-1111   cost terms of every (candidate, stage)
+//                                                                                   [stage parallel]
+//   init_cost_kernel        optim.c:1106-1111    ordered sum -> trajCosts
+//   multiplier_kernel       optim.c:1115-1136    multiplier update, outer-iteration reset
+//   linearize_kernel        optim.c:896-912      derivative records of every stage  [stage parallel]
+//   backward_kernel         optim.c:914-985      Riccati sweep, gains, box limits   [problem parallel]
+//   select_kernel           optim.c:840-873, 987-1006   ordered cost sums, first improving step
+//                                                wins, mu schedule, relative-change stop
+//   accept_kernel           optim.c:844-848      copy the winning candidate         [stage parallel]
+//   finalize_kernel         optim.c:1145-1149    termination flag
 //
 // Data layout: structure of arrays, problem index fastest — a warp of consecutive
 // problems reads/writes 256 contiguous bytes for every (stage, component).
+//
+// What is sequential stays sequential per problem (dynamics chain, Riccati recursion,
+// cost summation order t = 0..T then end cost, first-hit line search); everything that
+// the reference evaluates stage by stage without a dependency is evaluated stage
+// parallel.  Derivative entries that are identically 0 or 1 for the model are neither
+// stored nor multiplied: skipping `+ 0*v` and `1*v` leaves every sum bit-identical.
 #pragma once
 
 #include <cstdint>
@@ -29,7 +42,9 @@ template <typename M>
 struct Dims {
     static constexpr int X = M::X, U = M::U, C = M::C;
     static constexpr int Cs = C > 0 ? C : 1;
-    // derivative block of one stage
+    static constexpr int NSC = M::NUM_STAGE_CONSTS;
+    static constexpr int NSCs = NSC > 0 ? NSC : 1;
+    // dense derivative record of one stage (the layout of the fx..lux views)
     static constexpr int OFF_FX = 0;
     static constexpr int OFF_FU = OFF_FX + X * X;
     static constexpr int OFF_LX = OFF_FU + X * U;
@@ -37,62 +52,97 @@ struct Dims {
     static constexpr int OFF_LXX = OFF_LU + U;
     static constexpr int OFF_LUU = OFF_LXX + X * X;
     static constexpr int OFF_LUX = OFF_LUU + U * U;
-    static constexpr int STRIDE = OFF_LUX + U * X;
+    static constexpr int DENSE = OFF_LUX + U * X;
+    static constexpr int COMPACT = M::DERIV_COMPACT > 0 ? M::DERIV_COMPACT : 1;
+    static_assert(DENSE == M::DERIV_DENSE, "generated layout does not match the solver's");
 };
 
 // Scratch carved out of tplb_batch.workspace.
 struct Workspace {
-    double* deriv;       // [t_max][STRIDE][B]
-    double* cand_x;      // [8][t_max+1][X][B]
-    double* cand_u;      // [8][t_max][U][B]
-    double* cand_cost;   // [8][B]
-    int32_t* winner;     // [B]  index of the accepted alpha, -1 = none
-    int32_t* running;    // [B]  inner loop still active
+    double* stage_consts;  // [t_max+1][NSC][S]
+    double* deriv;         // [t_max][COMPACT][B]   compact derivative records
+    double* cand_x;        // [8][t_max+1][X][B]    line-search candidates
+    double* cand_u;        // [8][t_max][U][B]
+    double* cost_terms;    // [8][t_max+1][B]       stage costs (and end cost) of every candidate
+    double* cand_cost;     // [8][B]
+    int32_t* winner;       // [B]  index of the accepted alpha, -1 = none
+    int32_t* running;      // [B]  inner loop still active
+    int32_t* counters;     // [3][B] work the reference would have done in this update():
+                           //        linearisations, backward sweeps, sequential rollouts
 };
 
 __host__ __device__ inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
 
 template <typename M>
-__host__ __device__ inline Workspace carve(void* base, int B, int t_max, size_t* total = nullptr) {
+__host__ __device__ inline Workspace carve(void* base, int B, int S, int t_max, size_t* total = nullptr) {
     using D = Dims<M>;
     char* p = static_cast<char*>(base);
     size_t off = 0;
     Workspace w;
-    w.deriv = reinterpret_cast<double*>(p + off);     off += align_up(sizeof(double) * (size_t)t_max * D::STRIDE * B);
-    w.cand_x = reinterpret_cast<double*>(p + off);    off += align_up(sizeof(double) * (size_t)kAlphas * (t_max + 1) * D::X * B);
-    w.cand_u = reinterpret_cast<double*>(p + off);    off += align_up(sizeof(double) * (size_t)kAlphas * t_max * D::U * B);
-    w.cand_cost = reinterpret_cast<double*>(p + off); off += align_up(sizeof(double) * (size_t)kAlphas * B);
-    w.winner = reinterpret_cast<int32_t*>(p + off);   off += align_up(sizeof(int32_t) * (size_t)B);
-    w.running = reinterpret_cast<int32_t*>(p + off);  off += align_up(sizeof(int32_t) * (size_t)B);
+    auto take = [&](size_t bytes) { char* r = p + off; off += align_up(bytes); return r; };
+    w.stage_consts = reinterpret_cast<double*>(take(sizeof(double) * (size_t)(t_max + 1) * D::NSCs * S));
+    w.deriv = reinterpret_cast<double*>(take(sizeof(double) * (size_t)t_max * D::COMPACT * B));
+    w.cand_x = reinterpret_cast<double*>(take(sizeof(double) * (size_t)kAlphas * (t_max + 1) * D::X * B));
+    w.cand_u = reinterpret_cast<double*>(take(sizeof(double) * (size_t)kAlphas * t_max * D::U * B));
+    w.cost_terms = reinterpret_cast<double*>(take(sizeof(double) * (size_t)kAlphas * (t_max + 1) * B));
+    w.cand_cost = reinterpret_cast<double*>(take(sizeof(double) * (size_t)kAlphas * B));
+    w.winner = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)B));
+    w.running = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)B));
+    w.counters = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)3 * B));
     if (total) *total = off;
     return w;
 }
 
-__device__ __forceinline__ ParamView<double> param_view(const tplb_batch& q, int b) {
+__device__ __forceinline__ ParamView<double> param_view_scene(const tplb_batch& q, int scene) {
     ParamView<double> P;
     P.scalars = q.scalars;
     P.arrays = q.arrays;
     P.len = q.array_len;
     P.num_scenes = q.scenes;
-    P.scene = __ldg(q.scene_index + b);
+    P.scene = scene;
     return P;
+}
+
+template <typename M>
+__device__ __forceinline__ void load_stage_consts(const tplb_batch& q, const Workspace& ws, int scene, int t,
+                                                  double* sc) {
+    constexpr int NSC = M::NUM_STAGE_CONSTS;
+#pragma unroll
+    for (int j = 0; j < NSC; ++j) sc[j] = __ldg(ws.stage_consts + ((size_t)t * NSC + j) * q.scenes + scene);
+}
+
+// ---------------------------------------------------------------------------------
+// stage constants: thread per (scene, stage)
+// ---------------------------------------------------------------------------------
+template <typename M>
+__global__ void stage_constants_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
+    constexpr int NSC = M::NUM_STAGE_CONSTS;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;                                   // 0..T
+    if (s >= q.scenes) return;
+    if (NSC == 0) return;
+    const ParamView<double> P = param_view_scene(q, s);
+    double sc[Dims<M>::NSCs];
+    M::stage_constants(P, (double)t, q.dt, sc);
+#pragma unroll
+    for (int j = 0; j < NSC; ++j) ws.stage_consts[((size_t)t * NSC + j) * q.scenes + s] = sc[j];
 }
 
 // ---------------------------------------------------------------------------------
 // integrators (optim.c:657-730); ctDynamics sees the same (t, dt) at all sub-stages
 // ---------------------------------------------------------------------------------
-template <typename M, typename R, typename PV>
-__device__ __forceinline__ void step_state(const PV& P, const R* x, const R* u, R t, R h, int scheme, R* out) {
+template <typename M, int kScheme, typename R, typename PV>
+__device__ __forceinline__ void step_state(const PV& P, const R* x, const R* u, const R* sc, R t, R h, R* out) {
     constexpr int X = M::X;
     R k1[X], k2[X], y[X];
-    M::ct_dynamics(P, x, u, t, h, k1);
-    if (scheme == TPLB_EULER) {
+    M::ct_dynamics(P, x, u, sc, t, h, k1);
+    if constexpr (kScheme == TPLB_EULER) {
 #pragma unroll
         for (int i = 0; i < X; ++i) out[i] = x[i] + k1[i] * h;
-    } else if (scheme == TPLB_HEUN) {
+    } else if constexpr (kScheme == TPLB_HEUN) {
 #pragma unroll
         for (int i = 0; i < X; ++i) y[i] = x[i] + k1[i] * h;
-        M::ct_dynamics(P, y, u, t, h, k2);
+        M::ct_dynamics(P, y, u, sc, t, h, k2);
         const R hh = h / R(2);
 #pragma unroll
         for (int i = 0; i < X; ++i) out[i] = x[i] + (k1[i] + k2[i]) * hh;
@@ -101,13 +151,13 @@ __device__ __forceinline__ void step_state(const PV& P, const R* x, const R* u, 
         const R hh = h / R(2);
 #pragma unroll
         for (int i = 0; i < X; ++i) y[i] = x[i] + k1[i] * hh;
-        M::ct_dynamics(P, y, u, t, h, k2);
+        M::ct_dynamics(P, y, u, sc, t, h, k2);
 #pragma unroll
         for (int i = 0; i < X; ++i) y[i] = x[i] + k2[i] * hh;
-        M::ct_dynamics(P, y, u, t, h, k3);
+        M::ct_dynamics(P, y, u, sc, t, h, k3);
 #pragma unroll
         for (int i = 0; i < X; ++i) y[i] = x[i] + k3[i] * h;
-        M::ct_dynamics(P, y, u, t, h, k4);
+        M::ct_dynamics(P, y, u, sc, t, h, k4);
         const R h6 = h / R(6);
 #pragma unroll
         for (int i = 0; i < X; ++i) {
@@ -121,45 +171,155 @@ __device__ __forceinline__ void step_state(const PV& P, const R* x, const R* u, 
 }
 
 // ---------------------------------------------------------------------------------
-// initial rollout: x[t+1] = F(x[t], u[t]), trajCosts = sum_t l + l_end
+// rollouts — the only part of the forward pass that is a chain in t.
+//   kInit   : x[t+1] = F(x[t], u[t]) written in place (optim.c:1101-1107); block = PB problems
+//             (reads q.x[0] and q.u only, so the in-place write of x[t+1] is safe under __ldg)
+//   !kInit  : line search, block = PB problems x 8 step sizes; threadIdx.x = problem
+//             (coalesced), threadIdx.y = i with alpha_i = 1 / 10^i (optim.c:863);
+//             candidates go to ws.cand_x / ws.cand_u (the reference's next_x / next_u)
+// ---------------------------------------------------------------------------------
+template <typename M, int PB, bool kInit, int kScheme>
+__global__ void __launch_bounds__(PB * (kInit ? 1 : kAlphas))
+rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
+    using D = Dims<M>;
+    constexpr int X = D::X, U = D::U, NSC = D::NSC;
+    const int ai = kInit ? 0 : threadIdx.y;
+    const int b = blockIdx.x * PB + threadIdx.x;
+    const int B = q.batch;
+    if (b >= B) return;
+    if (kInit) {
+        ws.counters[b] = 0;
+        ws.counters[(size_t)B + b] = 0;
+        ws.counters[(size_t)2 * B + b] = 1;                      // the initial rollout itself
+    } else if (!ws.running[b]) {
+        return;
+    }
+    const int T = q.horizon;
+    const int scene = __ldg(q.scene_index + b);
+    const ParamView<double> P = param_view_scene(q, scene);
+    const bool second_order = q.use_quadratic_terms != 0;
+
+    double tens = 1.0;
+    for (int i = 0; i < ai; ++i) tens *= 10.0;
+    const double alpha = 1.0 / tens;
+
+    double* cx = kInit ? q.x + b : ws.cand_x + (size_t)ai * (q.t_max + 1) * X * B + b;
+    double* cu = kInit ? nullptr : ws.cand_u + (size_t)ai * q.t_max * U * B + b;
+
+    // Everything stage t needs from memory, fetched one stage ahead so that the
+    // load latency overlaps the dynamics chain of the previous stage.
+    struct Inputs {
+        double u[U], k[U], hi[U], lo[U], K[U][X], xref[X], sc[D::NSCs];
+    };
+    auto fetch = [&](int t, Inputs& in) {
+#pragma unroll
+        for (int d = 0; d < U; ++d) {
+            const size_t idx = ((size_t)t * U + d) * B + b;
+            in.u[d] = __ldg(q.u + idx);
+            if (!kInit) {
+                in.k[d] = __ldg(q.k + idx);
+                in.hi[d] = __ldg(q.u_max + idx);
+                in.lo[d] = __ldg(q.u_min + idx);
+                if (second_order) {
+#pragma unroll
+                    for (int j = 0; j < X; ++j) in.K[d][j] = __ldg(q.K + ((size_t)t * U * X + d * X + j) * B + b);
+                }
+            }
+        }
+        if (!kInit) {
+#pragma unroll
+            for (int j = 0; j < X; ++j) in.xref[j] = __ldg(q.x + ((size_t)t * X + j) * B + b);
+        }
+#pragma unroll
+        for (int j = 0; j < NSC; ++j) in.sc[j] = __ldg(ws.stage_consts + ((size_t)t * NSC + j) * q.scenes + scene);
+    };
+
+    double xn[X], xnext[X], un[U];
+#pragma unroll
+    for (int i = 0; i < X; ++i) {
+        xn[i] = q.x[(size_t)i * B + b];
+        if (!kInit) cx[(size_t)i * B] = xn[i];
+    }
+    Inputs cur, nxt;
+    fetch(0, nxt);
+    for (int t = 0; t < T; ++t) {
+        cur = nxt;
+        if (t + 1 < T) fetch(t + 1, nxt);
+#pragma unroll
+        for (int d = 0; d < U; ++d) {
+            if (kInit) {
+                un[d] = cur.u[d];
+            } else if (second_order) {
+                double v = cur.k[d] * alpha + cur.u[d];
+#pragma unroll
+                for (int j = 0; j < X; ++j) v += cur.K[d][j] * (xn[j] - cur.xref[j]);
+                const double capped = (cur.hi[d] < v) ? cur.hi[d] : v;     // optim.c:755-758
+                un[d] = (cur.lo[d] > capped) ? cur.lo[d] : capped;
+            } else {
+                un[d] = cur.u[d] - cur.k[d] * alpha;                       // optim.c:803-804
+            }
+            if (!kInit) cu[((size_t)t * U + d) * B] = un[d];
+        }
+        step_state<M, kScheme>(P, xn, un, cur.sc, (double)t, q.dt, xnext);
+#pragma unroll
+        for (int i = 0; i < X; ++i) {
+            xn[i] = xnext[i];
+            cx[((size_t)(t + 1) * X + i) * B] = xnext[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// cost terms of every (candidate, stage): stage cost for t < T, end cost for t == T.
+// grid (ceil(B/128), T+1, candidates).  Candidate a of problem b is read from
+// xs + a*x_stride, us + a*u_stride (the initial rollout passes q.x / q.u, 1 candidate).
 // ---------------------------------------------------------------------------------
 template <typename M>
-__global__ void rollout_init_kernel(const __grid_constant__ tplb_batch q) {
+__global__ void stage_cost_kernel(const __grid_constant__ tplb_batch q, Workspace ws,
+                                  const double* xs, const double* us, size_t x_stride, size_t u_stride,
+                                  int check_running) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U, C = D::C;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    const int a = blockIdx.z;
     const int B = q.batch;
     if (b >= B) return;
-    const ParamView<double> P = param_view(q, b);
+    if (check_running && !ws.running[b]) return;
+    const int T = q.horizon;
+    const int scene = __ldg(q.scene_index + b);
+    const ParamView<double> P = param_view_scene(q, scene);
+    const double* xa = xs + a * x_stride + b;
+    const double* ua = us + a * u_stride + b;
 
-    double w[D::Cs];
+    double x[X], sc[D::NSCs], c;
 #pragma unroll
-    for (int c = 0; c < C; ++c) w[c] = q.barrier_weight[(size_t)c * B + b];
-
-    double x[X], xn[X], u[U], lam[D::Cs];
+    for (int i = 0; i < X; ++i) x[i] = xa[((size_t)t * X + i) * B];
+    load_stage_consts<M>(q, ws, scene, t, sc);
+    if (t < T) {
+        double u[U], lam[D::Cs], w[D::Cs];
 #pragma unroll
-    for (int i = 0; i < X; ++i) x[i] = q.x[(size_t)i * B + b];
+        for (int i = 0; i < U; ++i) u[i] = ua[((size_t)t * U + i) * B];
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) {
+            lam[cc] = q.lagrange_multiplier[((size_t)t * C + cc) * B + b];
+            w[cc] = q.barrier_weight[(size_t)cc * B + b];
+        }
+        M::stage_cost(P, x, u, lam, w, sc, (double)t, q.dt, &c);
+    } else {
+        M::end_cost(P, x, sc, (double)T, q.dt, &c);
+    }
+    ws.cost_terms[((size_t)a * (q.t_max + 1) + t) * B + b] = c;
+}
 
+// trajCosts of the initial rollout: sum in the reference's order (optim.c:1099-1111)
+__global__ void init_cost_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int B = q.batch;
+    if (b >= B) return;
     double total = 0.0;
     const int T = q.horizon;
-    for (int t = 0; t < T; ++t) {
-#pragma unroll
-        for (int i = 0; i < U; ++i) u[i] = q.u[((size_t)t * U + i) * B + b];
-#pragma unroll
-        for (int c = 0; c < C; ++c) lam[c] = q.lagrange_multiplier[((size_t)t * C + c) * B + b];
-        step_state<M>(P, x, u, (double)t, q.dt, q.integrator_type, xn);
-        double c;
-        M::stage_cost(P, x, u, lam, w, (double)t, q.dt, &c);
-        total += c;
-#pragma unroll
-        for (int i = 0; i < X; ++i) {
-            x[i] = xn[i];
-            q.x[((size_t)(t + 1) * X + i) * B + b] = xn[i];
-        }
-    }
-    double ce;
-    M::end_cost(P, x, (double)T, q.dt, &ce);
-    total += ce;
+    for (int t = 0; t <= T; ++t) total += ws.cost_terms[(size_t)t * B + b];
     q.traj_costs[b] = total;
 }
 
@@ -182,8 +342,9 @@ __global__ void multiplier_kernel(const __grid_constant__ tplb_batch q, Workspac
         ws.running[b] = 1;
     }
     if (C == 0) return;
-    const ParamView<double> P = param_view(q, b);
-    double x[X], u[U], lam[D::Cs], w[D::Cs], g[D::Cs];
+    const int scene = __ldg(q.scene_index + b);
+    const ParamView<double> P = param_view_scene(q, scene);
+    double x[X], u[U], lam[D::Cs], w[D::Cs], g[D::Cs], sc[D::NSCs];
 #pragma unroll
     for (int i = 0; i < X; ++i) x[i] = q.x[((size_t)t * X + i) * B + b];
 #pragma unroll
@@ -194,7 +355,8 @@ __global__ void multiplier_kernel(const __grid_constant__ tplb_batch q, Workspac
         w[c] = q.barrier_weight[(size_t)c * B + b];
         g[c] = 0.0;
     }
-    M::constraints(P, x, u, lam, w, (double)t, q.dt, g);
+    load_stage_consts<M>(q, ws, scene, t, sc);
+    M::constraints(P, x, u, lam, w, sc, (double)t, q.dt, g);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         double v = lam[c] + w[c] * g[c];
@@ -205,7 +367,10 @@ __global__ void multiplier_kernel(const __grid_constant__ tplb_batch q, Workspac
 }
 
 // ---------------------------------------------------------------------------------
-// linearisation / quadratisation of every stage — thread per (problem, stage)
+// linearisation / quadratisation of every stage — thread per (problem, stage).
+// Only entries that are not identically 0/1 are stored (compact record).
+// kForce: every problem (tplb_linearize); otherwise only running problems whose
+// trajectory changed (optim.c:896).
 // ---------------------------------------------------------------------------------
 template <typename M, bool kForce>
 __global__ void linearize_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
@@ -216,9 +381,10 @@ __global__ void linearize_kernel(const __grid_constant__ tplb_batch q, Workspace
     const int B = q.batch;
     if (b >= B) return;
     if (!kForce && !(ws.running[b] && q.trajectory_changed[b])) return;
-    const ParamView<double> P = param_view(q, b);
+    const int scene = __ldg(q.scene_index + b);
+    const ParamView<double> P = param_view_scene(q, scene);
 
-    double x[X], u[U], lam[D::Cs], w[D::Cs];
+    double x[X], u[U], lam[D::Cs], w[D::Cs], sc[D::NSCs];
 #pragma unroll
     for (int i = 0; i < X; ++i) x[i] = q.x[((size_t)t * X + i) * B + b];
 #pragma unroll
@@ -228,20 +394,39 @@ __global__ void linearize_kernel(const __grid_constant__ tplb_batch q, Workspace
         lam[c] = q.lagrange_multiplier[((size_t)t * C + c) * B + b];
         w[c] = q.barrier_weight[(size_t)c * B + b];
     }
-    double blk[D::STRIDE];
+    load_stage_consts<M>(q, ws, scene, t, sc);
+    double blk[D::DENSE];
     if (q.use_quadratic_terms) {
-        M::linearize(P, x, u, lam, w, (double)t, q.dt,
+        M::linearize(P, x, u, lam, w, sc, (double)t, q.dt,
                      blk + D::OFF_FX, blk + D::OFF_FU, blk + D::OFF_LX, blk + D::OFF_LU,
                      blk + D::OFF_LXX, blk + D::OFF_LUU, blk + D::OFF_LUX);
     } else {
 #pragma unroll
-        for (int e = D::OFF_LXX; e < D::STRIDE; ++e) blk[e] = 0.0;
-        M::dynamics_jacobians(P, x, u, (double)t, q.dt, blk + D::OFF_FX, blk + D::OFF_FU);
-        M::cost_gradients(P, x, u, lam, w, (double)t, q.dt, blk + D::OFF_LX, blk + D::OFF_LU);
+        for (int e = D::OFF_LXX; e < D::DENSE; ++e) blk[e] = 0.0;
+        M::dynamics_jacobians(P, x, u, sc, (double)t, q.dt, blk + D::OFF_FX, blk + D::OFF_FU);
+        M::cost_gradients(P, x, u, lam, w, sc, (double)t, q.dt, blk + D::OFF_LX, blk + D::OFF_LU);
     }
-    double* out = ws.deriv + (size_t)t * D::STRIDE * B + b;
+    double* out = ws.deriv + (size_t)t * D::COMPACT * B + b;
 #pragma unroll
-    for (int e = 0; e < D::STRIDE; ++e) out[(size_t)e * B] = blk[e];
+    for (int e = 0; e < D::DENSE; ++e)
+        if (M::deriv_owner(e)) out[(size_t)M::deriv_slot(e) * B] = blk[e];
+}
+
+// compact -> dense records for the fx..lux views (optim.c:1663-1669), thread per (problem, stage)
+template <typename M>
+__global__ void expand_derivatives_kernel(const __grid_constant__ tplb_batch q, Workspace ws, double* dense) {
+    using D = Dims<M>;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    const int B = q.batch;
+    if (b >= B) return;
+    const double* in = ws.deriv + (size_t)t * D::COMPACT * B + b;
+    double* out = dense + (size_t)t * D::DENSE * B + b;
+#pragma unroll
+    for (int e = 0; e < D::DENSE; ++e) {
+        const int s = M::deriv_slot(e);
+        out[(size_t)e * B] = s >= 0 ? in[(size_t)s * B] : (s == -2 ? 1.0 : 0.0);
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -284,44 +469,75 @@ __device__ __forceinline__ void control_gains(const double (&Quu)[U][U], const d
     }
 }
 
+// acc += a * v where `slot` is the compile-time structure of a: -1 -> a == 0, -2 -> a == 1
+__device__ __forceinline__ void madd(double& acc, int slot, double a, double v) {
+    if (slot == -1) return;
+    if (slot == -2) acc += v;
+    else acc += a * v;
+}
+
 // ---------------------------------------------------------------------------------
-// backward Riccati sweep — thread per problem, value function in registers
+// backward Riccati sweep — thread per problem, value function in registers.
+// The next stage's compact record is prefetched while the current one is processed.
 // ---------------------------------------------------------------------------------
 template <typename M>
 __global__ void __launch_bounds__(128)
 backward_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteration) {
     using D = Dims<M>;
-    constexpr int X = D::X, U = D::U;
+    constexpr int X = D::X, U = D::U, NC = D::COMPACT;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int B = q.batch;
     if (b >= B) return;
     if (!ws.running[b]) return;
     q.iterations[b] = iteration + 1;             // optim.c:894
+    ws.counters[b] += q.trajectory_changed[b] ? 1 : 0;
+    ws.counters[(size_t)B + b] += 1;
     q.trajectory_changed[b] = 0;                 // optim.c:911 (linearize_kernel ran just before)
-    const ParamView<double> P = param_view(q, b);
+    const int scene = __ldg(q.scene_index + b);
+    const ParamView<double> P = param_view_scene(q, scene);
     const int T = q.horizon;
     const double mu = q.mu[b];
 
     double Vx[X], Vxx[X][X];
     {
-        double xT[X];
+        double xT[X], sc[D::NSCs];
 #pragma unroll
         for (int i = 0; i < X; ++i) xT[i] = q.x[((size_t)T * X + i) * B + b];
-        M::end_derivatives(P, xT, (double)T, q.dt, Vx, &Vxx[0][0]);
+        load_stage_consts<M>(q, ws, scene, T, sc);
+        M::end_derivatives(P, xT, sc, (double)T, q.dt, Vx, &Vxx[0][0]);
     }
 
-    for (int t = T - 1; t >= 0; --t) {
-        const double* blk = ws.deriv + (size_t)t * D::STRIDE * B + b;
-        auto ld = [&](int e) { return blk[(size_t)e * B]; };
-
-        double A[X][X], Bm[X][U];
+    double rec[NC], nxt[NC], ub[U], hib[U], lob[U], nub[U], nhib[U], nlob[U];
+    auto fetch = [&](int t, double* r, double* uu, double* hh, double* ll) {
+        const double* blk = ws.deriv + (size_t)t * NC * B + b;
 #pragma unroll
-        for (int i = 0; i < X; ++i) {
+        for (int s = 0; s < M::DERIV_COMPACT; ++s) r[s] = blk[(size_t)s * B];
 #pragma unroll
-            for (int j = 0; j < X; ++j) A[i][j] = ld(D::OFF_FX + i * X + j);
-#pragma unroll
-            for (int j = 0; j < U; ++j) Bm[i][j] = ld(D::OFF_FU + i * U + j);
+        for (int d = 0; d < U; ++d) {
+            const size_t idx = ((size_t)t * U + d) * B + b;
+            uu[d] = q.u[idx];
+            hh[d] = q.u_max[idx];
+            ll[d] = q.u_min[idx];
         }
+    };
+    fetch(T - 1, nxt, nub, nhib, nlob);
+
+    for (int t = T - 1; t >= 0; --t) {
+#pragma unroll
+        for (int s = 0; s < NC; ++s) rec[s] = nxt[s];
+#pragma unroll
+        for (int d = 0; d < U; ++d) { ub[d] = nub[d]; hib[d] = nhib[d]; lob[d] = nlob[d]; }
+        if (t > 0) fetch(t - 1, nxt, nub, nhib, nlob);
+
+        // dense entry e of the record: stored value, or the constant the structure says
+        auto val = [&](int e) {
+            const int s = M::deriv_slot(e);
+            return s >= 0 ? rec[s] : (s == -2 ? 1.0 : 0.0);
+        };
+#define A_(i, j) val(D::OFF_FX + (i) * X + (j))
+#define SA_(i, j) M::deriv_slot(D::OFF_FX + (i) * X + (j))
+#define B_(i, j) val(D::OFF_FU + (i) * U + (j))
+#define SB_(i, j) M::deriv_slot(D::OFF_FU + (i) * U + (j))
 
         double Qx[X], Qu[U], Qxx[X][X], Quu[U][U], Qux[U][X];
         double VA[X][X], VB[X][U];
@@ -330,15 +546,15 @@ backward_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteratio
         for (int i = 0; i < X; ++i) {                        // Qx = lx + A' Vx
             double acc = 0.0;
 #pragma unroll
-            for (int r = 0; r < X; ++r) acc += A[r][i] * Vx[r];
-            Qx[i] = ld(D::OFF_LX + i) + acc;
+            for (int r = 0; r < X; ++r) madd(acc, SA_(r, i), A_(r, i), Vx[r]);
+            Qx[i] = val(D::OFF_LX + i) + acc;
         }
 #pragma unroll
         for (int i = 0; i < U; ++i) {                        // Qu = lu + B' Vx
             double acc = 0.0;
 #pragma unroll
-            for (int r = 0; r < X; ++r) acc += Bm[r][i] * Vx[r];
-            Qu[i] = ld(D::OFF_LU + i) + acc;
+            for (int r = 0; r < X; ++r) madd(acc, SB_(r, i), B_(r, i), Vx[r]);
+            Qu[i] = val(D::OFF_LU + i) + acc;
         }
 #pragma unroll
         for (int i = 0; i < X; ++i) {                        // VA = Vxx A, VB = Vxx B
@@ -346,14 +562,14 @@ backward_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteratio
             for (int j = 0; j < X; ++j) {
                 double acc = 0.0;
 #pragma unroll
-                for (int r = 0; r < X; ++r) acc += Vxx[i][r] * A[r][j];
+                for (int r = 0; r < X; ++r) madd(acc, SA_(r, j), A_(r, j), Vxx[i][r]);
                 VA[i][j] = acc;
             }
 #pragma unroll
             for (int j = 0; j < U; ++j) {
                 double acc = 0.0;
 #pragma unroll
-                for (int r = 0; r < X; ++r) acc += Vxx[i][r] * Bm[r][j];
+                for (int r = 0; r < X; ++r) madd(acc, SB_(r, j), B_(r, j), Vxx[i][r]);
                 VB[i][j] = acc;
             }
         }
@@ -363,37 +579,41 @@ backward_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteratio
             for (int j = 0; j <= i; ++j) {
                 double acc = 0.0;
 #pragma unroll
-                for (int r = 0; r < X; ++r) acc += A[r][i] * VA[r][j];
+                for (int r = 0; r < X; ++r) madd(acc, SA_(r, i), A_(r, i), VA[r][j]);
                 Qxx[i][j] = acc;
                 Qxx[j][i] = acc;
             }
 #pragma unroll
         for (int i = 0; i < X; ++i)
 #pragma unroll
-            for (int j = 0; j < X; ++j) Qxx[i][j] = ld(D::OFF_LXX + i * X + j) + Qxx[i][j];
+            for (int j = 0; j < X; ++j) Qxx[i][j] = val(D::OFF_LXX + i * X + j) + Qxx[i][j];
 #pragma unroll
         for (int i = 0; i < U; ++i)                          // Quu = luu + B' VB (lower triangle mirrored)
 #pragma unroll
             for (int j = 0; j <= i; ++j) {
                 double acc = 0.0;
 #pragma unroll
-                for (int r = 0; r < X; ++r) acc += Bm[r][i] * VB[r][j];
+                for (int r = 0; r < X; ++r) madd(acc, SB_(r, i), B_(r, i), VB[r][j]);
                 Quu[i][j] = acc;
                 Quu[j][i] = acc;
             }
 #pragma unroll
         for (int i = 0; i < U; ++i)
 #pragma unroll
-            for (int j = 0; j < U; ++j) Quu[i][j] = ld(D::OFF_LUU + i * U + j) + Quu[i][j];
+            for (int j = 0; j < U; ++j) Quu[i][j] = val(D::OFF_LUU + i * U + j) + Quu[i][j];
 #pragma unroll
         for (int i = 0; i < U; ++i)                          // Qux = lux + B' VA
 #pragma unroll
             for (int j = 0; j < X; ++j) {
                 double acc = 0.0;
 #pragma unroll
-                for (int r = 0; r < X; ++r) acc += Bm[r][i] * VA[r][j];
-                Qux[i][j] = ld(D::OFF_LUX + i * X + j) + acc;
+                for (int r = 0; r < X; ++r) madd(acc, SB_(r, i), B_(r, i), VA[r][j]);
+                Qux[i][j] = val(D::OFF_LUX + i * X + j) + acc;
             }
+#undef A_
+#undef SA_
+#undef B_
+#undef SB_
 
         double k[U], K[U][X];
         control_gains<X, U>(Quu, Qu, Qux, mu, k, K);
@@ -401,17 +621,14 @@ backward_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteratio
         // box limits on the feed-forward step (optim.c:950-963)
 #pragma unroll
         for (int d = 0; d < U; ++d) {
-            const double ud = q.u[((size_t)t * U + d) * B + b];
-            const double cand = ud + k[d];
-            const double hi = q.u_max[((size_t)t * U + d) * B + b];
-            const double lo = q.u_min[((size_t)t * U + d) * B + b];
-            if (cand > hi) {
-                k[d] = hi - ud;
+            const double cand = ub[d] + k[d];
+            if (cand > hib[d]) {
+                k[d] = hib[d] - ub[d];
 #pragma unroll
                 for (int j = 0; j < X; ++j) K[d][j] = 0.0;
             }
-            if (cand < lo) {
-                k[d] = lo - ud;
+            if (cand < lob[d]) {
+                k[d] = lob[d] - ub[d];
 #pragma unroll
                 for (int j = 0; j < X; ++j) K[d][j] = 0.0;
             }
@@ -472,33 +689,42 @@ __global__ void backward_first_order_kernel(const __grid_constant__ tplb_batch q
     if (b >= B) return;
     if (!ws.running[b]) return;
     q.iterations[b] = iteration + 1;
+    ws.counters[b] += q.trajectory_changed[b] ? 1 : 0;
+    ws.counters[(size_t)B + b] += 1;
     q.trajectory_changed[b] = 0;
-    const ParamView<double> P = param_view(q, b);
+    const int scene = __ldg(q.scene_index + b);
+    const ParamView<double> P = param_view_scene(q, scene);
     const int T = q.horizon;
     double Vx[X];
     {
-        double xT[X], Vxx[X * X];
+        double xT[X], Vxx[X * X], sc[D::NSCs];
 #pragma unroll
         for (int i = 0; i < X; ++i) xT[i] = q.x[((size_t)T * X + i) * B + b];
-        M::end_derivatives(P, xT, (double)T, q.dt, Vx, Vxx);
+        load_stage_consts<M>(q, ws, scene, T, sc);
+        M::end_derivatives(P, xT, sc, (double)T, q.dt, Vx, Vxx);
     }
     for (int t = T - 1; t >= 0; --t) {
-        const double* blk = ws.deriv + (size_t)t * D::STRIDE * B + b;
-        auto ld = [&](int e) { return blk[(size_t)e * B]; };
+        const double* blk = ws.deriv + (size_t)t * D::COMPACT * B + b;
+        auto val = [&](int e) {
+            const int s = M::deriv_slot(e);
+            return s >= 0 ? blk[(size_t)s * B] : (s == -2 ? 1.0 : 0.0);
+        };
         double Qx[X];
 #pragma unroll
         for (int i = 0; i < X; ++i) {
             double acc = 0.0;
 #pragma unroll
-            for (int r = 0; r < X; ++r) acc += ld(D::OFF_FX + r * X + i) * Vx[r];
-            Qx[i] = ld(D::OFF_LX + i) + acc;
+            for (int r = 0; r < X; ++r)
+                madd(acc, M::deriv_slot(D::OFF_FX + r * X + i), val(D::OFF_FX + r * X + i), Vx[r]);
+            Qx[i] = val(D::OFF_LX + i) + acc;
         }
 #pragma unroll
         for (int i = 0; i < U; ++i) {
             double acc = 0.0;
 #pragma unroll
-            for (int r = 0; r < X; ++r) acc += ld(D::OFF_FU + r * U + i) * Vx[r];
-            const double gq = ld(D::OFF_LU + i) + acc;
+            for (int r = 0; r < X; ++r)
+                madd(acc, M::deriv_slot(D::OFF_FU + r * U + i), val(D::OFF_FU + r * U + i), Vx[r]);
+            const double gq = val(D::OFF_LU + i) + acc;
             const size_t idx = ((size_t)t * U + i) * B + b;
             const double ui = q.u[idx];
             double kk = gq;
@@ -514,110 +740,61 @@ __global__ void backward_first_order_kernel(const __grid_constant__ tplb_batch q
 }
 
 // ---------------------------------------------------------------------------------
-// line search: the 8 step sizes alpha_i = 10^-i roll out concurrently.
-// Block = PB problems x 8 step sizes; threadIdx.x = problem (coalesced), threadIdx.y = i.
-// The lowest i whose cost passes `testImprovement` wins, exactly what the reference's
-// sequential early-exit loop selects (optim.c:861-869).
+// line-search decision — block = PB problems x 8 candidates.  Costs are summed in the reference's
+// order (t = 0..T-1, then the end cost; optim.c:741-789); the lowest i whose cost
+// passes `testImprovement` wins, which is what the sequential early-exit loop of
+// the reference selects (optim.c:861-869).  Then the regularisation schedule and the
+// relative-change stop test (optim.c:987-1006).
 // ---------------------------------------------------------------------------------
-template <typename M, int PB>
+template <int PB>
 __global__ void __launch_bounds__(PB * kAlphas)
-line_search_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
-    using D = Dims<M>;
-    constexpr int X = D::X, U = D::U, C = D::C;
-    __shared__ double s_cost[kAlphas][PB];
-
-    const int lane = threadIdx.x;
-    const int ai = threadIdx.y;
+select_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
+    __shared__ double s_total[kAlphas][PB];
+    const int lane = threadIdx.x, a = threadIdx.y;
     const int b = blockIdx.x * PB + lane;
     const int B = q.batch;
-    const bool live = (b < B) && ws.running[b];
+    const bool live = b < B && ws.running[b];
     const int T = q.horizon;
-
-    // alpha = 1.0 / pow(10, i)   (optim.c:863)
-    double tens = 1.0;
-    for (int i = 0; i < ai; ++i) tens *= 10.0;
-    const double alpha = 1.0 / tens;
-
     double total = 0.0;
     if (live) {
-        const ParamView<double> P = param_view(q, b);
-        double w[D::Cs];
+        const double* terms = ws.cost_terms + (size_t)a * (q.t_max + 1) * B + b;
+        int t = 0;
+        for (; t + 8 <= T + 1; t += 8) {                     // loads in flight together, adds in order
+            double c[8];
 #pragma unroll
-        for (int c = 0; c < C; ++c) w[c] = q.barrier_weight[(size_t)c * B + b];
-
-        double* cx = ws.cand_x + (size_t)ai * (q.t_max + 1) * X * B + b;
-        double* cu = ws.cand_u + (size_t)ai * q.t_max * U * B + b;
-
-        double xn[X], xnext[X], un[U], lam[D::Cs];
+            for (int j = 0; j < 8; ++j) c[j] = terms[(size_t)(t + j) * B];
 #pragma unroll
-        for (int i = 0; i < X; ++i) {
-            xn[i] = q.x[(size_t)i * B + b];
-            cx[(size_t)i * B] = xn[i];
+            for (int j = 0; j < 8; ++j) total += c[j];
         }
-        const bool second_order = q.use_quadratic_terms != 0;
-        for (int t = 0; t < T; ++t) {
-#pragma unroll
-            for (int d = 0; d < U; ++d) {
-                const size_t idx = ((size_t)t * U + d) * B + b;
-                if (second_order) {
-                    double v = q.k[idx] * alpha + q.u[idx];
-#pragma unroll
-                    for (int j = 0; j < X; ++j)
-                        v += q.K[((size_t)t * U * X + d * X + j) * B + b] *
-                             (xn[j] - q.x[((size_t)t * X + j) * B + b]);
-                    const double hi = q.u_max[idx], lo = q.u_min[idx];
-                    const double capped = (hi < v) ? hi : v;           // optim.c:755-758
-                    un[d] = (lo > capped) ? lo : capped;
-                } else {
-                    un[d] = q.u[idx] - q.k[idx] * alpha;               // optim.c:803-804
-                }
-                cu[((size_t)t * U + d) * B] = un[d];
-            }
-#pragma unroll
-            for (int c = 0; c < C; ++c) lam[c] = q.lagrange_multiplier[((size_t)t * C + c) * B + b];
-            step_state<M>(P, xn, un, (double)t, q.dt, q.integrator_type, xnext);
-            double c;
-            M::stage_cost(P, xn, un, lam, w, (double)t, q.dt, &c);
-            total += c;
-#pragma unroll
-            for (int i = 0; i < X; ++i) {
-                xn[i] = xnext[i];
-                cx[((size_t)(t + 1) * X + i) * B] = xnext[i];
-            }
-        }
-        double ce;
-        M::end_cost(P, xn, (double)T, q.dt, &ce);
-        total += ce;
-        ws.cand_cost[(size_t)ai * B + b] = total;
+        for (; t <= T; ++t) total += terms[(size_t)t * B];
+        ws.cand_cost[(size_t)a * B + b] = total;
     }
-    s_cost[ai][lane] = total;
+    s_total[a][lane] = total;
     __syncthreads();
-
-    if (ai != 0 || b >= B) return;
+    if (a != 0 || b >= B) return;
     if (!live) {                                             // stopped earlier: nothing to accept
         ws.winner[b] = -1;
         return;
     }
-
-    // testImprovement (optim.c:842) for i = 0..7 in order
     const double before = q.traj_costs[b];
     int win = -1;
+    double now = before;
 #pragma unroll
     for (int i = kAlphas - 1; i >= 0; --i) {
-        const double c = s_cost[i][lane];
-        if (c < before && isfinite(c) && c >= 0.0) win = i;
+        const double c = s_total[i][lane];
+        if (c < before && isfinite(c) && c >= 0.0) {         // testImprovement, optim.c:842
+            win = i;
+            now = c;
+        }
     }
     ws.winner[b] = win;
-    double now = before;
-    double a_used = 1e-7;                                    // last step tried when none passes
+    ws.counters[(size_t)2 * B + b] += (win >= 0) ? win + 1 : kAlphas;   // rollouts a sequential search runs
     {
-        double tn = 1.0;
+        double tn = 1.0;                                     // alpha of the last step tried (optim.c:863)
         for (int i = 0; i < (win < 0 ? kAlphas - 1 : win); ++i) tn *= 10.0;
-        a_used = 1.0 / tn;
+        q.alpha[b] = 1.0 / tn;
     }
-    q.alpha[b] = a_used;
     if (win >= 0) {
-        now = s_cost[win][lane];
         q.traj_costs[b] = now;
         q.trajectory_changed[b] = 1;
         q.improved[b] = 1;
@@ -706,7 +883,8 @@ __global__ void shift_kernel(const __grid_constant__ tplb_batch q, int amount, c
 }
 
 // ---------------------------------------------------------------------------------
-// point evaluations of the dynamics (optim.c:1512-1652)
+// point evaluations of the dynamics (optim.c:1512-1652); stage constants are
+// evaluated on the fly for the requested (t, dt)
 // ---------------------------------------------------------------------------------
 template <typename M>
 __global__ void dynamics_kernel(const __grid_constant__ tplb_batch q, const double* x_in, const double* u_in,
@@ -715,19 +893,18 @@ __global__ void dynamics_kernel(const __grid_constant__ tplb_batch q, const doub
     constexpr int X = M::X, U = M::U;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    ParamView<double> P;
-    P.scalars = q.scalars;
-    P.arrays = q.arrays;
-    P.len = q.array_len;
-    P.num_scenes = q.scenes;
-    P.scene = scene_of_point ? scene_of_point[i] : ((n == q.batch && q.scene_index) ? q.scene_index[i] : 0);
-    double x[X], u[U], out[X];
+    const int scene = scene_of_point ? scene_of_point[i] : ((n == q.batch && q.scene_index) ? q.scene_index[i] : 0);
+    const ParamView<double> P = param_view_scene(q, scene);
+    double x[X], u[U], out[X], sc[Dims<M>::NSCs];
 #pragma unroll
     for (int j = 0; j < X; ++j) x[j] = x_in[(size_t)j * n + i];
 #pragma unroll
     for (int j = 0; j < U; ++j) u[j] = u_in[(size_t)j * n + i];
-    if (continuous) M::ct_dynamics(P, x, u, (double)t, dt, out);
-    else step_state<M>(P, x, u, (double)t, dt, q.integrator_type, out);
+    M::stage_constants(P, (double)t, dt, sc);
+    if (continuous) M::ct_dynamics(P, x, u, sc, (double)t, dt, out);
+    else if (q.integrator_type == TPLB_EULER) step_state<M, TPLB_EULER>(P, x, u, sc, (double)t, dt, out);
+    else if (q.integrator_type == TPLB_HEUN) step_state<M, TPLB_HEUN>(P, x, u, sc, (double)t, dt, out);
+    else step_state<M, TPLB_RK4>(P, x, u, sc, (double)t, dt, out);
 #pragma unroll
     for (int j = 0; j < X; ++j) x_out[(size_t)j * n + i] = out[j];
 }
