@@ -1,0 +1,139 @@
+"""Host-side mirror of the reference `Optim` interface (tpl_b200/batched.py): shapes,
+construction defaults, setters, horizon clamp, deepcopy / __getstate__ — exercised
+on CPU buffers.  Compute entry points must refuse to run without CUDA."""
+
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from tests import common
+from tpl_b200 import _cabi, scenarios as sc
+from tpl_b200.batched import BatchedOptim
+
+
+@pytest.fixture()
+def lateral(solver_libs):
+    return BatchedOptim(solver_libs["lateral_profile"], batch=4, horizon_max=60, device="cpu")
+
+
+@pytest.fixture()
+def mpc_time(solver_libs):
+    return BatchedOptim(solver_libs["trajectory_tracking_mpc_time"], batch=3, scenes=1,
+                        horizon_max=50, device="cpu")
+
+
+def test_construction_defaults(lateral):
+    """optim.c:1894-1921, SURVEY.md appendix G11."""
+    o = lateral
+    assert (o.dt, o.horizon, o.max_iterations, o.max_lg_iterations) == (0.05, 20, 5, 1)
+    assert o.min_rel_cost_change == 1e-6 and o.use_quadratic_terms and o.opt_start == 0
+    assert bool(torch.isinf(o.lg_mult_limit).all()) and bool((o.barrier_weight == 1).all())
+    o.horizon = 40
+    assert o.u_max[0, 18:23].tolist() == [float("inf"), float("inf"), 0.0, 0.0, 0.0]
+    assert o.u_min[0, 18:23].tolist() == [-float("inf"), -float("inf"), 0.0, 0.0, 0.0]
+    assert bool((o.x == 0).all()) and bool((o.lagrange_multiplier == 0).all())
+
+
+def test_shapes_are_squeezed_like_the_reference(lateral, mpc_time):
+    """optim.c:1314-1325: U == 1 gives u of shape (T,) per problem."""
+    o = lateral
+    o.horizon = 40
+    assert o.x.shape == (4, 41, 2) and o.u.shape == (4, 40) and o.K.shape == (4, 40, 2)
+    assert o.fx.shape == (4, 40, 2, 2) and o.fu.shape == (4, 40, 2) and o.luu.shape == (4, 40)
+    assert o.lux.shape == (4, 40, 2) and o.lagrange_multiplier.shape == (4, 40, 2)
+    assert o[1].x.shape == (41, 2) and o[1].u.shape == (40,)
+    m = mpc_time
+    m.horizon = 30
+    assert m.x.shape == (3, 31, 6) and m.u.shape == (3, 30, 2) and m.K.shape == (3, 30, 2, 6)
+    assert m.fx.shape == (3, 30, 6, 6) and m.fu.shape == (3, 30, 6, 2) and m.lux.shape == (3, 30, 2, 6)
+    assert m.barrier_weight.shape == (3, 4) and m.int_step.shape == (3, 31)
+
+
+def test_horizon_is_clamped(lateral, solver_libs):
+    lateral.horizon = 1000                      # optim.c:1726-1734, capacity 60 here
+    assert lateral.horizon == 60 and lateral.T == 60
+    lateral.horizon = -5
+    assert lateral.horizon == 1
+    full = BatchedOptim(solver_libs["ref_line_smoother_k"], batch=1, device="cpu")
+    full.horizon = 1000
+    assert full.horizon == 299
+    assert full.lagrange_multiplier.shape == (1, 299, 0)          # C == 0 model
+
+
+def test_setters_broadcast_and_write_through(lateral):
+    o = lateral
+    o.horizon = 30
+    o.u_min = -2.5                              # scalar broadcast (path_optim.py:129)
+    o.u_max[:, :5] = 0.0                        # in-place write through a view (path_optim.py:164)
+    assert bool((o.u_min == -2.5).all()) and bool((o.u_max[:, :5] == 0).all())
+    o.u = np.arange(30.0)                       # (T,) broadcast over the batch (velocity_optim.py:170)
+    assert torch.equal(o.u[2], torch.arange(30.0, dtype=torch.float64))
+    o.x[:, 0] = torch.tensor([[1.0, 2.0]], dtype=torch.float64)
+    assert o[3].x[0].tolist() == [1.0, 2.0]
+    o[1].u = np.ones(30)
+    assert bool((o.u[1] == 1).all()) and bool((o.u[0] == torch.arange(30.0, dtype=torch.float64)).all())
+    o.lg_mult_limit = 0.0                       # path_optim.py:102
+    o.barrier_weight[:] = 1000.0                # path_optim.py:103
+    assert bool((o.lg_mult_limit == 0).all()) and bool((o.barrier_weight == 1000).all())
+    o.mu_step = 3
+    assert o.mu_step.tolist() == [3, 3, 3, 3]
+    with pytest.raises(AttributeError):
+        o[0].horizon = 5
+
+
+def test_params_scalars_and_arrays(mpc_time):
+    p = mpc_time.params
+    assert p.slots[:3] == ["pd", "pv", "pdelta"] and "ref_x" in p.slots
+    p.pd = 5.0
+    p.ref_x = np.linspace(0.0, 1.0, 80)         # (L,) shared by all scenes
+    assert p.pd.tolist() == [5.0] and p.ref_x.shape == (1, 80)
+    with pytest.raises(AttributeError):
+        p.nonexistent = 1.0
+    with pytest.raises(ValueError):
+        p.ref_x = np.zeros((2, 80))             # wrong number of scenes
+    with pytest.raises(ValueError):
+        mpc_time.scene_index = np.array([0, 1, 0])   # scene 1 does not exist
+    state = mpc_time.__getstate__()
+    assert sorted(state) == sorted(["u_min", "u_max", "horizon", "opt_start", "barrier_weight",
+                                    "lg_mult_limit", "max_iterations", "max_lg_iterations", "step",
+                                    "use_quadratic_terms", "params"])     # optim.c:1806-1819
+    assert state["params"]["pd"].tolist() == [5.0]
+
+
+def test_deepcopy_is_independent(lateral):
+    pb = sc.lateral(4, horizon=40)
+    o = sc.apply_to_batched(lateral, pb)
+    c = copy.deepcopy(o)
+    assert torch.equal(c.x, o.x) and torch.equal(c.params.k_ref, o.params.k_ref) and c.horizon == o.horizon
+    c.x[:, 0] = 7.0
+    c.params.w_d = 9.0
+    assert not torch.equal(c.x, o.x) and float(o.params.w_d[0]) == 0.2
+
+
+def test_slots_match_reference(lateral):
+    assert lateral.slots[:6] == ["step", "opt_start", "horizon", "int_step", "x", "u"]
+    assert "min_rel_cost_change" in lateral.slots and len(lateral.slots) == 42
+
+
+def test_no_cpu_fallback(lateral, solver_libs):
+    for call in (lateral.update, lateral.linearize, lambda: lateral.shift(1),
+                 lambda: lateral.dynamics(np.zeros(2), np.zeros(1), 0, 0.1),
+                 lambda: lateral.argmin_groups(2)):
+        with pytest.raises(_cabi.SolverError):
+            call()
+    if not torch.cuda.is_available():
+        with pytest.raises(_cabi.SolverError):
+            BatchedOptim(solver_libs["lateral_profile"], batch=2)
+    with pytest.raises(OSError):
+        _cabi.load("/nonexistent/libtplb200_x.so")
+
+
+def test_scenario_batches_are_seeded(solver_libs):
+    a, b = sc.mpc_time(8, horizon=20), sc.mpc_time(8, horizon=20)
+    assert np.array_equal(a.x0, b.x0) and np.array_equal(a.arrays["ref_x"], b.arrays["ref_x"])
+    sub = a.subset([5, 2])
+    assert sub.batch == 2 and np.array_equal(sub.x0[0], a.x0[5]) and sub.scenes == 2
+    ms = sc.mpc_time(8, scenes=2, horizon=20)
+    assert ms.scenes == 2 and ms.scene_of.tolist() == [0, 0, 0, 0, 1, 1, 1, 1]

@@ -6,6 +6,7 @@
 // sequence of kernel launches; per-problem progress (running / trajectory_changed /
 // winner) lives on the device, so no launch depends on a device->host read.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "solver.cuh"
@@ -161,15 +162,19 @@ int32_t tplb_update_profiled(const tplb_batch* qp, void* stream_, float* ms_by_c
 namespace {
 
 constexpr int PB = 32;                                     // problems per rollout / select block
-
 template <bool kInit>
 void launch_rollout(const tplb_batch& q, const tplb::Workspace& ws, cudaStream_t st) {
     const dim3 grid((q.batch + PB - 1) / PB), block(PB, kInit ? 1 : tplb::kAlphas);
+    const bool dense = !kInit && q.batch >= 16384;         // enough blocks to want 2 per SM
+#define TPLB_ROLLOUT(SCHEME)                                                                          \
+    if (dense) tplb::rollout_kernel<Model, PB, kInit, SCHEME, kInit ? 1 : 2><<<grid, block, 0, st>>>(q, ws); \
+    else tplb::rollout_kernel<Model, PB, kInit, SCHEME, 1><<<grid, block, 0, st>>>(q, ws)
     switch (q.integrator_type) {
-        case TPLB_EULER: tplb::rollout_kernel<Model, PB, kInit, TPLB_EULER><<<grid, block, 0, st>>>(q, ws); break;
-        case TPLB_HEUN: tplb::rollout_kernel<Model, PB, kInit, TPLB_HEUN><<<grid, block, 0, st>>>(q, ws); break;
-        default: tplb::rollout_kernel<Model, PB, kInit, TPLB_RK4><<<grid, block, 0, st>>>(q, ws); break;
+        case TPLB_EULER: TPLB_ROLLOUT(TPLB_EULER); break;
+        case TPLB_HEUN: TPLB_ROLLOUT(TPLB_HEUN); break;
+        default: TPLB_ROLLOUT(TPLB_RK4); break;
     }
+#undef TPLB_ROLLOUT
 }
 
 int run_update(const tplb_batch* qp, void* stream_, Profiler& prof) {
@@ -192,7 +197,7 @@ int run_update(const tplb_batch* qp, void* stream_, Profiler& prof) {
     prof.before();
     launch_rollout<true>(q, ws, st);
     tplb::stage_cost_kernel<Model><<<dim3(sgx, T + 1, 1), sb, 0, st>>>(q, ws, q.x, q.u, 0, 0, 0);
-    tplb::init_cost_kernel<<<(B + sb - 1) / sb, sb, 0, st>>>(q, ws);
+    tplb::init_cost_kernel<<<sgx, sb, 0, st>>>(q, ws);
     prof.after(TPLB_K_ROLLOUT_INIT);
 
     int lg = 0;
@@ -226,7 +231,7 @@ int run_update(const tplb_batch* qp, void* stream_, Profiler& prof) {
         }
     }
     prof.before();
-    tplb::finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(q, lg);
+    tplb::finalize_kernel<<<sgx, sb, 0, st>>>(q, lg);
     prof.after(TPLB_K_FINALIZE);
     return check_launch("tplb_update");
 }

@@ -177,9 +177,11 @@ __device__ __forceinline__ void step_state(const PV& P, const R* x, const R* u, 
 //   !kInit  : line search, block = PB problems x 8 step sizes; threadIdx.x = problem
 //             (coalesced), threadIdx.y = i with alpha_i = 1 / 10^i (optim.c:863);
 //             candidates go to ws.cand_x / ws.cand_u (the reference's next_x / next_u)
+//   kMinBlocks : 2 caps registers at 128 so two blocks fit per SM — more resident warps for
+//             batches that fill the chip; 1 keeps everything in registers for small batches
 // ---------------------------------------------------------------------------------
-template <typename M, int PB, bool kInit, int kScheme>
-__global__ void __launch_bounds__(PB * (kInit ? 1 : kAlphas))
+template <typename M, int PB, bool kInit, int kScheme, int kMinBlocks>
+__global__ void __launch_bounds__(PB * (kInit ? 1 : kAlphas), kMinBlocks)
 rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U, NSC = D::NSC;
