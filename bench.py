@@ -35,14 +35,16 @@ UNIT = "solves/s"
 # Algorithmic flops per stage (add/sub/mul/div = 1,
 # interpolation call = 9; transcendental calls are listed separately as "special").
 FLOPS = {
-    "trajectory_tracking_mpc_time": dict(lin=366, bwd=1717, fwd=225, con=9, sp_lin=22, sp_fwd=12),
+    # fwd = feedback (X+2U+2UX = 34) + HEUN (2 F_ct + 5X = 70) + stage cost (84 + 4 lookups x 9 + 1 = 121)
+    "trajectory_tracking_mpc_time": dict(lin=366, bwd=1717, fwd=225, fwd_chain=104, fwd_cost=121, con=9,
+                                         sp_lin=22, sp_fwd=12),
 }
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="problems per GPU")
@@ -67,7 +69,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -148,7 +150,7 @@ def run_reference_arm(a):
         return
     from tpl_b200 import scenarios as sc
     cores = os.cpu_count() or 1
-    n = max(cores * 4, 128)
+    n = max(cores * 32, 512)
     pb = sc.mpc_time(batch=n, horizon=a.horizon, max_iterations=a.iterations, forced=True)
     for _ in range(a.warmup):
         cpu_throughput(pb, max(cores, 16), cores)
@@ -300,10 +302,13 @@ def run_ours(a):
         torch.cuda.synchronize()
         lin, bwd, roll = (int(c.sum().item()) for c in opt.work_counters())
         F = FLOPS[MODEL]
+        # algorithmic flops by kernel class; the forward pass (F_fwd per stage and rollout the
+        # reference would run sequentially) splits into the dynamics chain and the stage cost
         flops = {
             "linearize": lin * T * F["lin"],
             "backward": bwd * T * F["bwd"],
-            "line_search": (roll - B) * T * F["fwd"],
+            "rollout": (roll - B) * T * F["fwd_chain"],
+            "stage_cost": (roll - B) * T * F["fwd_cost"],
             "rollout_init": B * T * F["fwd"],
             "multiplier": B * T * F["con"] * pb.max_lg_iterations,
         }
