@@ -136,7 +136,7 @@ typedef struct {
      *   cand_x       [8][t_max+1][X][B]         line-search candidates (next_x of each alpha)
      *   cand_u       [8][t_max][U][B]
      *   cost_terms   [8][t_max+1][B]            stage / end cost of every candidate and stage
-     *   cand_cost    [8][B], winner [B], running [B], counters [3][B]                      */
+     *   cand_cost    [8][B], winner [B], running [B], counters [3][B], pending [B] + count  */
     void* workspace;
     size_t workspace_bytes;
 
@@ -151,8 +151,6 @@ TPLB_API const char* tplb_last_error(void);
 
 /* Bytes of device scratch a batch of this shape needs. */
 TPLB_API size_t tplb_workspace_bytes(int32_t batch, int32_t scenes, int32_t t_max);
-/* Device address of the [8][B] candidate costs of the last line search. */
-TPLB_API void* tplb_workspace_cand_cost(void* workspace, int32_t batch, int32_t scenes, int32_t t_max);
 
 /* Device address of the [3][B] int32 work counters of the last update(): linearisations,
  * backward sweeps and the rollouts a sequential line search would have executed
@@ -175,10 +173,11 @@ enum {
     TPLB_K_MULTIPLIER = 2,    /* multiplier_kernel                                         */
     TPLB_K_LINEARIZE = 3,     /* linearize_kernel                                          */
     TPLB_K_BACKWARD = 4,      /* backward_kernel                                           */
-    TPLB_K_ROLLOUT = 5,       /* rollout_kernel<line search>: 8 step sizes                 */
-    TPLB_K_STAGE_COST = 6,    /* stage_cost_kernel on the 8 candidates                     */
-    TPLB_K_SELECT = 7,        /* select_kernel                                             */
-    TPLB_K_ACCEPT = 8,        /* accept_kernel                                             */
+    TPLB_K_ROLLOUT = 5,       /* rollout_kernel<line search>: the step-size candidates     */
+    TPLB_K_STAGE_COST = 6,    /* stage_cost_kernel on the candidates (rounds 1 and 2)      */
+    TPLB_K_SELECT = 7,        /* select_kernel (rounds 1 and 2)                            */
+    TPLB_K_ACCEPT = 8,        /* accept_kernel (after the last iteration; otherwise folded
+                                 into the next linearize_kernel)                           */
     TPLB_K_FINALIZE = 9,      /* finalize_kernel                                           */
     TPLB_NUM_KERNEL_CLASSES = 10
 };

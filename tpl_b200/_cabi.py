@@ -50,7 +50,7 @@ class Batch(C.Structure):
 #: every symbol include/tplb200.h declares (tests check the library exports all of them)
 EXPORTS = (
     "tplb_abi_version", "tplb_model", "tplb_last_error", "tplb_workspace_bytes",
-    "tplb_workspace_cand_cost", "tplb_workspace_counters",
+    "tplb_workspace_counters",
     "tplb_update", "tplb_update_profiled", "tplb_linearize", "tplb_expand_derivatives",
     "tplb_shift", "tplb_dynamics", "tplb_argmin_groups", "tplb_measure_fp64_tflops",
 )
@@ -69,8 +69,6 @@ def load(path):
     lib.tplb_last_error.restype = C.c_char_p
     lib.tplb_workspace_bytes.restype = C.c_size_t
     lib.tplb_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
-    lib.tplb_workspace_cand_cost.restype = C.c_void_p
-    lib.tplb_workspace_cand_cost.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
     lib.tplb_workspace_counters.restype = C.c_void_p
     lib.tplb_workspace_counters.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
     lib.tplb_update_profiled.restype = C.c_int32

@@ -261,6 +261,38 @@ def _lookup_fn(name, values, ctype="int"):
             f"    }}\n")
 
 
+def expand_trig_of_atan(expr):
+    """sin / cos of ``a + atan(z)`` by the angle-addition formulas:
+
+        cos(a + atan z) = (cos a - z sin a) / sqrt(1 + z^2)
+        sin(a + atan z) = (sin a + z cos a) / sqrt(1 + z^2)
+
+    The kinematic-bicycle models take the sine and cosine of heading + slip angle with
+    slip = atan(c tan(delta)).  Evaluated literally this is a chain of three dependent
+    transcendental calls (tan -> atan -> sincos) in the innermost recursion of the
+    rollout; rewritten, the atan disappears and sincos(heading) no longer waits for
+    tan(delta).  Mathematically identical, rounding differs by a few ulp."""
+    def rewrite(f):
+        arg = f.args[0]
+        if not isinstance(arg, sp.Add):
+            return f
+        atans = [t for t in arg.args if isinstance(t, sp.atan)]
+        neg = [t for t in arg.args if isinstance(t, sp.Mul) and t.args[0] == -1 and len(t.args) == 2
+               and isinstance(t.args[1], sp.atan)]
+        if len(atans) + len(neg) != 1:
+            return f
+        if atans:
+            z, rest = atans[0].args[0], arg - atans[0]
+        else:
+            z, rest = -neg[0].args[1].args[0], arg - neg[0]
+        r = 1 / sp.sqrt(1 + z**2)
+        if isinstance(f, sp.cos):
+            return (sp.cos(rest) - z * sp.sin(rest)) * r
+        return (sp.sin(rest) + z * sp.cos(rest)) * r
+
+    return expr.replace(lambda e: isinstance(e, (sp.sin, sp.cos)), rewrite)
+
+
 def hoist_stage_constants(d: Derivation):
     """Interpolation lookups whose arguments depend only on the stage index, the
     step and the parameters are constant per (scene, stage) for a whole solve
@@ -276,7 +308,8 @@ def hoist_stage_constants(d: Derivation):
                     calls.add(call)
     calls = sorted(calls, key=str)
     repl = {c: sp.Symbol(f"sc[{i}]") for i, c in enumerate(calls)}
-    routines = {n: (m.xreplace(repl) if m.shape[0] * m.shape[1] else m) for n, m in d.routines.items()}
+    routines = {n: (expand_trig_of_atan(m.xreplace(repl)) if m.shape[0] * m.shape[1] else m)
+                for n, m in d.routines.items()}
     return routines, calls
 
 

@@ -99,10 +99,6 @@ size_t tplb_workspace_bytes(int32_t batch, int32_t scenes, int32_t t_max) {
     return need;
 }
 
-void* tplb_workspace_cand_cost(void* workspace, int32_t batch, int32_t scenes, int32_t t_max) {
-    return tplb::carve<Model>(workspace, batch, scenes, t_max).cand_cost;
-}
-
 void* tplb_workspace_counters(void* workspace, int32_t batch, int32_t scenes, int32_t t_max) {
     return tplb::carve<Model>(workspace, batch, scenes, t_max).counters;
 }
@@ -162,19 +158,31 @@ int32_t tplb_update_profiled(const tplb_batch* qp, void* stream_, float* ms_by_c
 namespace {
 
 constexpr int PB = 32;                                     // problems per rollout / select block
+// rollouts of candidates [a_begin, a_begin + a_count) for every problem (list == NULL) or
+// for the problems of the pending list
 template <bool kInit>
-void launch_rollout(const tplb_batch& q, const tplb::Workspace& ws, cudaStream_t st) {
-    const dim3 grid((q.batch + PB - 1) / PB), block(PB, kInit ? 1 : tplb::kAlphas);
+void launch_rollout(const tplb_batch& q, const tplb::Workspace& ws, cudaStream_t st,
+                    int a_begin, int a_count, const int32_t* list) {
+    const dim3 grid((q.batch + PB - 1) / PB), block(PB, kInit ? 1 : a_count);
     const bool dense = !kInit && q.batch >= 16384;         // enough blocks to want 2 per SM
-#define TPLB_ROLLOUT(SCHEME)                                                                          \
-    if (dense) tplb::rollout_kernel<Model, PB, kInit, SCHEME, kInit ? 1 : 2><<<grid, block, 0, st>>>(q, ws); \
-    else tplb::rollout_kernel<Model, PB, kInit, SCHEME, 1><<<grid, block, 0, st>>>(q, ws)
+#define TPLB_ROLLOUT(SCHEME)                                                                            \
+    if (dense) tplb::rollout_kernel<Model, PB, kInit, SCHEME, kInit ? 1 : 2><<<grid, block, 0, st>>>(   \
+                   q, ws, a_begin, list);                                                               \
+    else tplb::rollout_kernel<Model, PB, kInit, SCHEME, 1><<<grid, block, 0, st>>>(q, ws, a_begin, list)
     switch (q.integrator_type) {
         case TPLB_EULER: TPLB_ROLLOUT(TPLB_EULER); break;
         case TPLB_HEUN: TPLB_ROLLOUT(TPLB_HEUN); break;
         default: TPLB_ROLLOUT(TPLB_RK4); break;
     }
 #undef TPLB_ROLLOUT
+}
+
+// Rollouts in two rounds as well once the batch fills the chip: the 6 small step sizes are
+// then rolled out only for the problems that need them.  Below that every phase is
+// latency-bound and rolling out all 8 at once is free.
+bool two_round_rollouts(int B) {
+    if (const char* e = std::getenv("TPLB_TWO_ROUND_ROLLOUTS")) return std::atoi(e) != 0;
+    return B >= 8192;
 }
 
 int run_update(const tplb_batch* qp, void* stream_, Profiler& prof) {
@@ -189,14 +197,16 @@ int run_update(const tplb_batch* qp, void* stream_, Profiler& prof) {
     const unsigned sgx = (B + sb - 1) / sb;
     const size_t cx_stride = (size_t)(q.t_max + 1) * Model::X * B;
     const size_t cu_stride = (size_t)q.t_max * Model::U * B;
+    constexpr int R1 = tplb::kRound1, R2 = tplb::kAlphas - tplb::kRound1;
+    const bool split_rollouts = two_round_rollouts(B);
 
     prof.before();
     tplb::stage_constants_kernel<Model><<<dim3((S + sb - 1) / sb, T + 1), sb, 0, st>>>(q, ws);
     prof.after(TPLB_K_STAGE_CONSTS);
 
     prof.before();
-    launch_rollout<true>(q, ws, st);
-    tplb::stage_cost_kernel<Model><<<dim3(sgx, T + 1, 1), sb, 0, st>>>(q, ws, q.x, q.u, 0, 0, 0);
+    launch_rollout<true>(q, ws, st, 0, 1, nullptr);
+    tplb::stage_cost_kernel<Model><<<dim3(sgx, T + 1, 1), sb, 0, st>>>(q, ws, q.x, q.u, 0, 0, 0, 0, nullptr);
     tplb::init_cost_kernel<<<sgx, sb, 0, st>>>(q, ws);
     prof.after(TPLB_K_ROLLOUT_INIT);
 
@@ -207,7 +217,8 @@ int run_update(const tplb_batch* qp, void* stream_, Profiler& prof) {
         prof.after(TPLB_K_MULTIPLIER);
         for (int s = 0; s < q.max_iterations; ++s) {
             prof.before();
-            tplb::linearize_kernel<Model, false><<<dim3(sgx, T), sb, 0, st>>>(q, ws);
+            if (s == 0) tplb::linearize_kernel<Model, false, false><<<dim3(sgx, T), sb, 0, st>>>(q, ws);
+            else tplb::linearize_kernel<Model, false, true><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
             prof.after(TPLB_K_LINEARIZE);
             prof.before();
             if (q.use_quadratic_terms)
@@ -215,16 +226,35 @@ int run_update(const tplb_batch* qp, void* stream_, Profiler& prof) {
             else
                 tplb::backward_first_order_kernel<Model><<<pgrid, pb, 0, st>>>(q, ws, s);
             prof.after(TPLB_K_BACKWARD);
+
+            // round 1: alpha = 1, 0.1
             prof.before();
-            launch_rollout<false>(q, ws, st);
+            if (split_rollouts) launch_rollout<false>(q, ws, st, 0, R1, nullptr);
+            else launch_rollout<false>(q, ws, st, 0, tplb::kAlphas, nullptr);
             prof.after(TPLB_K_ROLLOUT);
             prof.before();
-            tplb::stage_cost_kernel<Model><<<dim3(sgx, T + 1, tplb::kAlphas), sb, 0, st>>>(
-                q, ws, ws.cand_x, ws.cand_u, cx_stride, cu_stride, 1);
+            tplb::stage_cost_kernel<Model><<<dim3(sgx, T + 1, R1), sb, 0, st>>>(
+                q, ws, ws.cand_x, ws.cand_u, cx_stride, cu_stride, 1, 0, nullptr);
             prof.after(TPLB_K_STAGE_COST);
             prof.before();
-            tplb::select_kernel<PB><<<(B + PB - 1) / PB, dim3(PB, tplb::kAlphas), 0, st>>>(q, ws);
+            tplb::select_kernel<PB, 1><<<(B + PB - 1) / PB, dim3(PB, R1), 0, st>>>(q, ws);
             prof.after(TPLB_K_SELECT);
+
+            // round 2: alpha = 1e-2 .. 1e-7 for the problems still pending
+            if (split_rollouts) {
+                prof.before();
+                launch_rollout<false>(q, ws, st, R1, R2, ws.pending);
+                prof.after(TPLB_K_ROLLOUT);
+            }
+            prof.before();
+            tplb::stage_cost_kernel<Model><<<dim3(sgx, T + 1, R2), sb, 0, st>>>(
+                q, ws, ws.cand_x, ws.cand_u, cx_stride, cu_stride, 1, R1, ws.pending);
+            prof.after(TPLB_K_STAGE_COST);
+            prof.before();
+            tplb::select_kernel<PB, 2><<<(B + PB - 1) / PB, dim3(PB, R2), 0, st>>>(q, ws);
+            prof.after(TPLB_K_SELECT);
+        }
+        if (q.max_iterations > 0) {
             prof.before();
             tplb::accept_kernel<Model><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
             prof.after(TPLB_K_ACCEPT);
@@ -258,7 +288,7 @@ int32_t tplb_linearize(const tplb_batch* qp, void* stream_) {
     const tplb::Workspace ws = tplb::carve<Model>(q.workspace, q.batch, q.scenes, q.t_max);
     const dim3 grid((q.batch + 127) / 128, q.horizon);
     tplb::stage_constants_kernel<Model><<<dim3((q.scenes + 127) / 128, q.horizon + 1), 128, 0, st>>>(q, ws);
-    tplb::linearize_kernel<Model, true><<<grid, 128, 0, st>>>(q, ws);
+    tplb::linearize_kernel<Model, true, false><<<grid, 128, 0, st>>>(q, ws);
     tplb::expand_derivatives_kernel<Model><<<grid, 128, 0, st>>>(q, ws, q.deriv_dense);
     return check_launch("tplb_linearize");
 }

@@ -13,9 +13,12 @@
 //   multiplier_kernel       optim.c:1115-1136    multiplier update, outer-iteration reset
 //   linearize_kernel        optim.c:896-912      derivative records of every stage  [stage parallel]
 //   backward_kernel         optim.c:914-985      Riccati sweep, gains, box limits   [problem parallel]
-//   select_kernel           optim.c:840-873, 987-1006   ordered cost sums, first improving step
-//                                                wins, mu schedule, relative-change stop
+//   select_kernel<round>    optim.c:840-873, 987-1006   ordered cost sums, first improving step
+//                                                wins, mu schedule, relative-change stop.  Round 1
+//                                                looks at alpha = 1, 0.1; only problems where both
+//                                                fail go to round 2 (alpha = 1e-2 .. 1e-7)
 //   accept_kernel           optim.c:844-848      copy the winning candidate         [stage parallel]
+//                                                (folded into the next linearize_kernel inside the loop)
 //   finalize_kernel         optim.c:1145-1149    termination flag
 //
 // Data layout: structure of arrays, problem index fastest — a warp of consecutive
@@ -37,6 +40,13 @@
 namespace tplb {
 
 constexpr int kAlphas = TPLB_LINE_SEARCH_STEPS;
+constexpr int kRound1 = 2;      // step sizes of the first line-search round (alpha = 1, 0.1)
+
+// Problem handled by work item `idx`: the item itself, or an entry of the pending list.
+__device__ __forceinline__ int problem_of(const int32_t* list, const int32_t* count, int idx, int B) {
+    if (!list) return idx < B ? idx : -1;
+    return idx < *count ? list[idx] : -1;
+}
 
 template <typename M>
 struct Dims {
@@ -69,6 +79,8 @@ struct Workspace {
     int32_t* running;      // [B]  inner loop still active
     int32_t* counters;     // [3][B] work the reference would have done in this update():
                            //        linearisations, backward sweeps, sequential rollouts
+    int32_t* pending;      // [B]  problems whose round-1 step sizes all failed (unordered list)
+    int32_t* pending_count;// [1]
 };
 
 __host__ __device__ inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
@@ -89,6 +101,8 @@ __host__ __device__ inline Workspace carve(void* base, int B, int S, int t_max, 
     w.winner = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)B));
     w.running = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)B));
     w.counters = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)3 * B));
+    w.pending = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)B));
+    w.pending_count = reinterpret_cast<int32_t*>(take(sizeof(int32_t)));
     if (total) *total = off;
     return w;
 }
@@ -182,13 +196,13 @@ __device__ __forceinline__ void step_state(const PV& P, const R* x, const R* u, 
 // ---------------------------------------------------------------------------------
 template <typename M, int PB, bool kInit, int kScheme, int kMinBlocks>
 __global__ void __launch_bounds__(PB * (kInit ? 1 : kAlphas), kMinBlocks)
-rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
+rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int a_begin, const int32_t* list) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U, NSC = D::NSC;
-    const int ai = kInit ? 0 : threadIdx.y;
-    const int b = blockIdx.x * PB + threadIdx.x;
+    const int ai = kInit ? 0 : a_begin + threadIdx.y;      // blockDim.y = candidates of this launch
     const int B = q.batch;
-    if (b >= B) return;
+    const int b = problem_of(list, ws.pending_count, blockIdx.x * PB + threadIdx.x, B);
+    if (b < 0) return;
     if (kInit) {
         ws.counters[b] = 0;
         ws.counters[(size_t)B + b] = 0;
@@ -213,40 +227,46 @@ rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
     struct Inputs {
         double u[U], k[U], hi[U], lo[U], K[U][X], xref[X], sc[D::NSCs];
     };
+    const int iB = B;                                        // component stride inside a stage
     auto fetch = [&](int t, Inputs& in) {
+        const double* ut = q.u + (size_t)t * U * B + b;
 #pragma unroll
-        for (int d = 0; d < U; ++d) {
-            const size_t idx = ((size_t)t * U + d) * B + b;
-            in.u[d] = __ldg(q.u + idx);
-            if (!kInit) {
-                in.k[d] = __ldg(q.k + idx);
-                in.hi[d] = __ldg(q.u_max + idx);
-                in.lo[d] = __ldg(q.u_min + idx);
-                if (second_order) {
-#pragma unroll
-                    for (int j = 0; j < X; ++j) in.K[d][j] = __ldg(q.K + ((size_t)t * U * X + d * X + j) * B + b);
-                }
-            }
-        }
+        for (int d = 0; d < U; ++d) in.u[d] = __ldg(ut + d * iB);
         if (!kInit) {
+            const double* kt = q.k + (size_t)t * U * B + b;
+            const double* ht = q.u_max + (size_t)t * U * B + b;
+            const double* lt = q.u_min + (size_t)t * U * B + b;
 #pragma unroll
-            for (int j = 0; j < X; ++j) in.xref[j] = __ldg(q.x + ((size_t)t * X + j) * B + b);
+            for (int d = 0; d < U; ++d) {
+                in.k[d] = __ldg(kt + d * iB);
+                in.hi[d] = __ldg(ht + d * iB);
+                in.lo[d] = __ldg(lt + d * iB);
+            }
+            if (second_order) {
+                const double* Kt = q.K + (size_t)t * U * X * B + b;
+#pragma unroll
+                for (int d = 0; d < U; ++d)
+#pragma unroll
+                    for (int j = 0; j < X; ++j) in.K[d][j] = __ldg(Kt + (d * X + j) * iB);
+            }
+            const double* xt = q.x + (size_t)t * X * B + b;
+#pragma unroll
+            for (int j = 0; j < X; ++j) in.xref[j] = __ldg(xt + j * iB);
         }
+        const double* st = ws.stage_consts + (size_t)t * NSC * q.scenes + scene;
 #pragma unroll
-        for (int j = 0; j < NSC; ++j) in.sc[j] = __ldg(ws.stage_consts + ((size_t)t * NSC + j) * q.scenes + scene);
+        for (int j = 0; j < NSC; ++j) in.sc[j] = __ldg(st + j * q.scenes);
     };
 
-    double xn[X], xnext[X], un[U];
+    double xn[X];
 #pragma unroll
     for (int i = 0; i < X; ++i) {
         xn[i] = q.x[(size_t)i * B + b];
         if (!kInit) cx[(size_t)i * B] = xn[i];
     }
-    Inputs cur, nxt;
-    fetch(0, nxt);
-    for (int t = 0; t < T; ++t) {
-        cur = nxt;
-        if (t + 1 < T) fetch(t + 1, nxt);
+
+    auto stage = [&](int t, const Inputs& cur) {
+        double un[U], xnext[X];
 #pragma unroll
         for (int d = 0; d < U; ++d) {
             if (kInit) {
@@ -260,33 +280,51 @@ rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
             } else {
                 un[d] = cur.u[d] - cur.k[d] * alpha;                       // optim.c:803-804
             }
-            if (!kInit) cu[((size_t)t * U + d) * B] = un[d];
+        }
+        if (!kInit) {
+            double* cut = cu + (size_t)t * U * B;
+#pragma unroll
+            for (int d = 0; d < U; ++d) cut[d * iB] = un[d];
         }
         step_state<M, kScheme>(P, xn, un, cur.sc, (double)t, q.dt, xnext);
+        double* cxt = cx + (size_t)(t + 1) * X * B;
 #pragma unroll
         for (int i = 0; i < X; ++i) {
             xn[i] = xnext[i];
-            cx[((size_t)(t + 1) * X + i) * B] = xnext[i];
+            cxt[i * iB] = xnext[i];
         }
+    };
+
+    // two stages per trip with ping-pong input buffers: no register copies between stages
+    Inputs in0, in1;
+    fetch(0, in0);
+    int t = 0;
+    for (; t + 1 < T; t += 2) {
+        fetch(t + 1, in1);
+        stage(t, in0);
+        if (t + 2 < T) fetch(t + 2, in0);
+        stage(t + 1, in1);
     }
+    if (t < T) stage(t, in0);
 }
 
 // ---------------------------------------------------------------------------------
 // cost terms of every (candidate, stage): stage cost for t < T, end cost for t == T.
-// grid (ceil(B/128), T+1, candidates).  Candidate a of problem b is read from
+// grid (ceil(B/128), T+1, candidates of this launch).  Candidate a of problem b is read from
 // xs + a*x_stride, us + a*u_stride (the initial rollout passes q.x / q.u, 1 candidate).
+// `list` != NULL: work items are entries of the pending list (round 2 of the line search).
 // ---------------------------------------------------------------------------------
 template <typename M>
 __global__ void stage_cost_kernel(const __grid_constant__ tplb_batch q, Workspace ws,
                                   const double* xs, const double* us, size_t x_stride, size_t u_stride,
-                                  int check_running) {
+                                  int check_running, int a_begin, const int32_t* list) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U, C = D::C;
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int t = blockIdx.y;
-    const int a = blockIdx.z;
+    const int a = a_begin + blockIdx.z;
     const int B = q.batch;
-    if (b >= B) return;
+    const int b = problem_of(list, ws.pending_count, blockIdx.x * blockDim.x + threadIdx.x, B);
+    if (b < 0) return;
     if (check_running && !ws.running[b]) return;
     const int T = q.horizon;
     const int scene = __ldg(q.scene_index + b);
@@ -372,25 +410,59 @@ __global__ void multiplier_kernel(const __grid_constant__ tplb_batch q, Workspac
 // linearisation / quadratisation of every stage — thread per (problem, stage).
 // Only entries that are not identically 0/1 are stored (compact record).
 // kForce: every problem (tplb_linearize); otherwise only running problems whose
-// trajectory changed (optim.c:896).
+// trajectory changed (optim.c:896).  kAccept: first install the step the previous
+// line search accepted (the work of accept_kernel; grid has one extra row for x[T]).
 // ---------------------------------------------------------------------------------
-template <typename M, bool kForce>
-__global__ void linearize_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
+template <typename M, bool kForce, bool kAccept>
+__global__ void __launch_bounds__(128, 4)
+linearize_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U, C = D::C;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = blockIdx.y;
+    const int t = blockIdx.y;                                // 0..T-1 (0..T with kAccept)
     const int B = q.batch;
     if (b >= B) return;
+    const int T = q.horizon;
+
+    double x[X], u[U];
+    bool have = false;
+    if (kAccept) {
+        // the step accepted by the previous line search becomes the trajectory (optim.c:844-848)
+        const int win = ws.winner[b];
+        if (win >= 0) {
+            const double* cx = ws.cand_x + (size_t)win * (q.t_max + 1) * X * B + b;
+            const double* cu = ws.cand_u + (size_t)win * q.t_max * U * B + b;
+#pragma unroll
+            for (int i = 0; i < X; ++i) {
+                const size_t idx = ((size_t)t * X + i) * B + b;
+                x[i] = cx[((size_t)t * X + i) * B];
+                if (q.keep_previous) q.prev_x[idx] = q.x[idx];
+                q.x[idx] = x[i];
+            }
+            if (t < T) {
+#pragma unroll
+                for (int d = 0; d < U; ++d) {
+                    const size_t idx = ((size_t)t * U + d) * B + b;
+                    u[d] = cu[((size_t)t * U + d) * B];
+                    if (q.keep_previous) q.prev_k[idx] = q.k[idx];
+                    q.u[idx] = u[d];
+                }
+            }
+            have = true;
+        }
+        if (t >= T) return;
+    }
     if (!kForce && !(ws.running[b] && q.trajectory_changed[b])) return;
     const int scene = __ldg(q.scene_index + b);
     const ParamView<double> P = param_view_scene(q, scene);
 
-    double x[X], u[U], lam[D::Cs], w[D::Cs], sc[D::NSCs];
+    double lam[D::Cs], w[D::Cs], sc[D::NSCs];
+    if (!have) {
 #pragma unroll
-    for (int i = 0; i < X; ++i) x[i] = q.x[((size_t)t * X + i) * B + b];
+        for (int i = 0; i < X; ++i) x[i] = q.x[((size_t)t * X + i) * B + b];
 #pragma unroll
-    for (int i = 0; i < U; ++i) u[i] = q.u[((size_t)t * U + i) * B + b];
+        for (int i = 0; i < U; ++i) u[i] = q.u[((size_t)t * U + i) * B + b];
+    }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         lam[c] = q.lagrange_multiplier[((size_t)t * C + c) * B + b];
@@ -489,6 +561,7 @@ backward_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteratio
     constexpr int X = D::X, U = D::U, NC = D::COMPACT;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int B = q.batch;
+    if (b == 0) *ws.pending_count = 0;           // the line search of this iteration starts empty
     if (b >= B) return;
     if (!ws.running[b]) return;
     q.iterations[b] = iteration + 1;             // optim.c:894
@@ -688,6 +761,7 @@ __global__ void backward_first_order_kernel(const __grid_constant__ tplb_batch q
     constexpr int X = D::X, U = D::U;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int B = q.batch;
+    if (b == 0) *ws.pending_count = 0;
     if (b >= B) return;
     if (!ws.running[b]) return;
     q.iterations[b] = iteration + 1;
@@ -742,53 +816,16 @@ __global__ void backward_first_order_kernel(const __grid_constant__ tplb_batch q
 }
 
 // ---------------------------------------------------------------------------------
-// line-search decision — block = PB problems x 8 candidates.  Costs are summed in the reference's
+// line-search decision in two rounds.  Costs are summed in the reference's
 // order (t = 0..T-1, then the end cost; optim.c:741-789); the lowest i whose cost
 // passes `testImprovement` wins, which is what the sequential early-exit loop of
 // the reference selects (optim.c:861-869).  Then the regularisation schedule and the
 // relative-change stop test (optim.c:987-1006).
 // ---------------------------------------------------------------------------------
-template <int PB>
-__global__ void __launch_bounds__(PB * kAlphas)
-select_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
-    __shared__ double s_total[kAlphas][PB];
-    const int lane = threadIdx.x, a = threadIdx.y;
-    const int b = blockIdx.x * PB + lane;
+// everything the reference does once the search has ended for a problem (optim.c:849-851, 987-1006)
+__device__ __forceinline__ void conclude_line_search(const tplb_batch& q, const Workspace& ws, int b,
+                                                     int win, double before, double now) {
     const int B = q.batch;
-    const bool live = b < B && ws.running[b];
-    const int T = q.horizon;
-    double total = 0.0;
-    if (live) {
-        const double* terms = ws.cost_terms + (size_t)a * (q.t_max + 1) * B + b;
-        int t = 0;
-        for (; t + 8 <= T + 1; t += 8) {                     // loads in flight together, adds in order
-            double c[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) c[j] = terms[(size_t)(t + j) * B];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) total += c[j];
-        }
-        for (; t <= T; ++t) total += terms[(size_t)t * B];
-        ws.cand_cost[(size_t)a * B + b] = total;
-    }
-    s_total[a][lane] = total;
-    __syncthreads();
-    if (a != 0 || b >= B) return;
-    if (!live) {                                             // stopped earlier: nothing to accept
-        ws.winner[b] = -1;
-        return;
-    }
-    const double before = q.traj_costs[b];
-    int win = -1;
-    double now = before;
-#pragma unroll
-    for (int i = kAlphas - 1; i >= 0; --i) {
-        const double c = s_total[i][lane];
-        if (c < before && isfinite(c) && c >= 0.0) {         // testImprovement, optim.c:842
-            win = i;
-            now = c;
-        }
-    }
     ws.winner[b] = win;
     ws.counters[(size_t)2 * B + b] += (win >= 0) ? win + 1 : kAlphas;   // rollouts a sequential search runs
     {
@@ -817,6 +854,59 @@ select_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
         q.termination_condition[b] = 2;
         ws.running[b] = 0;
     }
+}
+
+// kRound == 1: block = PB problems x kRound1 candidates, every problem of the batch.
+// kRound == 2: block = PB pending problems x (8 - kRound1) candidates.
+template <int PB, int kRound>
+__global__ void __launch_bounds__(PB * (kRound == 1 ? kRound1 : kAlphas - kRound1))
+select_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
+    constexpr int NA = kRound == 1 ? kRound1 : kAlphas - kRound1;
+    constexpr int A0 = kRound == 1 ? 0 : kRound1;
+    __shared__ double s_total[NA][PB];
+    const int lane = threadIdx.x, a = A0 + threadIdx.y;
+    const int B = q.batch;
+    const int b = problem_of(kRound == 1 ? nullptr : ws.pending, ws.pending_count, blockIdx.x * PB + lane, B);
+    const bool live = b >= 0 && ws.running[b];
+    const int T = q.horizon;
+    double total = 0.0;
+    if (live) {
+        const double* terms = ws.cost_terms + (size_t)a * (q.t_max + 1) * B + b;
+        int t = 0;
+        for (; t + 8 <= T + 1; t += 8) {                     // loads in flight together, adds in order
+            double c[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) c[j] = terms[(size_t)(t + j) * B];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) total += c[j];
+        }
+        for (; t <= T; ++t) total += terms[(size_t)t * B];
+        ws.cand_cost[(size_t)a * B + b] = total;
+    }
+    s_total[threadIdx.y][lane] = total;
+    __syncthreads();
+    if (threadIdx.y != 0 || b < 0) return;
+    if (!live) {                                             // stopped earlier: nothing to accept
+        ws.winner[b] = -1;
+        return;
+    }
+    const double before = q.traj_costs[b];
+    int win = -1;
+    double now = before;
+#pragma unroll
+    for (int i = NA - 1; i >= 0; --i) {
+        const double c = s_total[i][lane];
+        if (c < before && isfinite(c) && c >= 0.0) {         // testImprovement, optim.c:842
+            win = A0 + i;
+            now = c;
+        }
+    }
+    if (kRound == 1 && win < 0) {                            // alpha = 1 and 0.1 failed: try the rest
+        ws.winner[b] = -1;
+        ws.pending[atomicAdd(ws.pending_count, 1)] = b;
+        return;
+    }
+    conclude_line_search(q, ws, b, win, before, now);
 }
 
 // copy the accepted candidate into x, u (and keep prev_x, prev_k) — thread per (problem, stage)
