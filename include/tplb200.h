@@ -209,6 +209,10 @@ TPLB_API int32_t tplb_dynamics(const tplb_batch* batch, const double* x_in, cons
 TPLB_API int32_t tplb_argmin_groups(const double* traj_costs, int32_t groups, int32_t per_group,
                            double* min_cost, int32_t* arg_min, void* stream);
 
+/* Diagnostic: evaluates the straight-line elementary functions the generated model code uses
+ * (csrc/fast_math.cuh) on n device values: fn 0 sin, 1 cos, 2 tan, 3 1/x, 4 1/sqrt(x), 5 sqrt(x). */
+TPLB_API int32_t tplb_selftest_math(int32_t fn, const double* x, int32_t n, double* out, void* stream);
+
 /* Peak of the FP64 pipe, measured with a register-resident DFMA loop on the current
  * device (the roofline denominator for this path); returns TFLOP/s, <0 on error. */
 TPLB_API double tplb_measure_fp64_tflops(int32_t repeats, void* stream);

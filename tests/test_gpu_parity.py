@@ -174,3 +174,33 @@ def test_full_size_properties(solver_libs):
     ref_mn, ref_am = q.traj_costs.view(-1, 64).min(dim=1)
     assert torch.equal(mn, ref_mn)
     assert torch.equal(am.long(), ref_am + torch.arange(64, device=am.device) * 64)
+
+
+def _ulp_error(got, want):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    ulp = np.spacing(np.abs(want))
+    return np.max(np.abs(got - want) / ulp)
+
+
+def test_fast_math_accuracy(solver_libs):
+    """csrc/fast_math.cuh against numpy (libm): the straight-line sin/cos/tan/1/x/rsqrt/sqrt the
+    generated model code calls stay within 2 ulp on their stated domains."""
+    import ctypes as C
+    from tpl_b200 import _cabi
+    lib = _cabi.load(solver_libs["lateral_profile"])
+    rng = np.random.default_rng(0)
+    n = 1 << 18
+    angles = np.concatenate([rng.uniform(-10.0, 10.0, n // 2), rng.uniform(-1e5, 1e5, n // 4),
+                             rng.uniform(-1e-3, 1e-3, n // 4)])
+    positive = np.concatenate([rng.uniform(1e-12, 1.0, n // 2), rng.uniform(1.0, 1e12, n // 2)])
+    signed = positive * rng.choice([-1.0, 1.0], n)
+    cases = [(0, angles, np.sin, 2.0), (1, angles, np.cos, 2.0), (2, angles, np.tan, 3.0),
+             (3, signed, lambda v: 1.0 / v, 1.0), (4, positive, lambda v: 1.0 / np.sqrt(v), 2.0),
+             (5, positive, np.sqrt, 1.0)]
+    stream = torch.cuda.current_stream().cuda_stream
+    for fn, xs, ref, bound in cases:
+        x = torch.from_numpy(xs).cuda()
+        out = torch.empty_like(x)
+        _cabi.check(lib, lib.tplb_selftest_math(fn, x.data_ptr(), x.numel(), out.data_ptr(), stream), "selftest")
+        err = _ulp_error(out.cpu().numpy(), ref(xs))
+        assert err <= bound, f"fn {fn}: {err:.2f} ulp"

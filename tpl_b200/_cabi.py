@@ -52,7 +52,8 @@ EXPORTS = (
     "tplb_abi_version", "tplb_model", "tplb_last_error", "tplb_workspace_bytes",
     "tplb_workspace_counters",
     "tplb_update", "tplb_update_profiled", "tplb_linearize", "tplb_expand_derivatives",
-    "tplb_shift", "tplb_dynamics", "tplb_argmin_groups", "tplb_measure_fp64_tflops",
+    "tplb_shift", "tplb_dynamics", "tplb_argmin_groups", "tplb_selftest_math",
+    "tplb_measure_fp64_tflops",
 )
 
 
@@ -83,6 +84,8 @@ def load(path):
                                   C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]
     lib.tplb_argmin_groups.restype = C.c_int32
     lib.tplb_argmin_groups.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.tplb_selftest_math.restype = C.c_int32
+    lib.tplb_selftest_math.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.tplb_measure_fp64_tflops.restype = C.c_double
     lib.tplb_measure_fp64_tflops.argtypes = [C.c_int32, C.c_void_p]
     if lib.tplb_abi_version() != ABI_VERSION:

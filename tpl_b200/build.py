@@ -31,6 +31,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-fno-gnu-unique",
     "--expt-relaxed-constexpr",
 ]
+if os.environ.get("TPLB_LIBDEVICE_MATH"):                  # A/B: CUDA libdevice sin/cos/tan/div/sqrt
+    NVCC_FLAGS.append("-DTPLB_LIBDEVICE_MATH")
 
 
 def default_lib_dir():
@@ -46,7 +48,7 @@ def nvcc_path():
 
 def _solver_sources_hash():
     h = hashlib.sha1()
-    for fn in ("solver.cuh", "device_math.cuh", "cabi.cu"):
+    for fn in ("solver.cuh", "device_math.cuh", "fast_math.cuh", "cabi.cu"):
         with open(os.path.join(CSRC, fn), "rb") as fd:
             h.update(fd.read())
     with open(os.path.join(PKG, "..", "include", "tplb200.h"), "rb") as fd:

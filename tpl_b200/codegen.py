@@ -57,8 +57,15 @@ class ModelPrinter(C99CodePrinter):
     made single-evaluation (``sq(a)`` instead of ``(a*a)``), typed literals, and
     parameter / interpolation access through the dialect."""
 
+    # CUDA dialect: straight-line elementary functions of csrc/fast_math.cuh (m_* resolve to
+    # them, or to libdevice when a library is built with -DTPLB_LIBDEVICE_MATH)
+    CUDA_FUNCTIONS = {"sin": "m_sin", "cos": "m_cos", "tan": "m_tan"}
+
     def __init__(self, deriv: Derivation, dialect: Dialect):
-        super().__init__({"allow_unknown_functions": True})
+        settings = {"allow_unknown_functions": True}
+        if dialect.name == "cuda":
+            settings["user_functions"] = dict(self.CUDA_FUNCTIONS)
+        super().__init__(settings)
         self.d = deriv
         self.dialect = dialect
         self.scalar_index = {n: i for i, n in enumerate(deriv.scalar_params)}
@@ -87,6 +94,9 @@ class ModelPrinter(C99CodePrinter):
         return self._lit("%d.0/%d.0" % (r.p, r.q))
 
     # -- powers ----------------------------------------------------------------
+    def _params_only(self, e):
+        return bool(e.free_symbols) and all(f.name in self.scalar_index for f in e.free_symbols)
+
     def _print_Pow(self, e):
         b, x = e.base, e.exp
         one = self._lit("1.0")
@@ -98,7 +108,7 @@ class ModelPrinter(C99CodePrinter):
         if x == -2:
             return "%s/sq(%s)" % (one, pb)
         if x == sp.Rational(1, 2) or x == 0.5:
-            return "sqrt(%s)" % pb
+            return "%s(%s)" % ("m_sqrt" if self.dialect.name == "cuda" else "sqrt", pb)
         if x == sp.Rational(-1, 2) or x == -0.5:
             return "%s/sqrt(%s)" % (one, pb)
         if x == sp.Rational(3, 2) or x == 1.5:
@@ -158,6 +168,27 @@ def _one_line(text):
     return re.sub(r"\s*\n\s*", " ", text)
 
 
+_RSQRT = sp.Function("m_rsqrt")
+_INV = sp.Function("m_inv")
+
+
+def _strength_reduce(printer, e):
+    """CUDA dialect only, applied to the already CSE'd expressions right before printing:
+
+    * ``b**(-1/2)``  -> ``m_rsqrt(b)``  (one MUFU + Newton steps instead of sqrt + divide);
+    * ``b**(-n)``    -> ``m_inv(b**n)``: every division becomes a multiplication by a
+      straight-line reciprocal.  Reciprocals of parameter-only expressions are loop invariant,
+      so the compiler hoists them out of the stage loops entirely.  (sympy prints negative
+      powers inside a product as a division, so this is a tree rewrite, not a printer hook.)
+
+    ``a * (1/b)`` differs from ``a / b`` by at most one ulp."""
+    e = e.replace(lambda p: isinstance(p, sp.Pow) and p.exp == sp.Rational(-1, 2),
+                  lambda p: _RSQRT(p.base))
+    e = e.replace(lambda p: isinstance(p, sp.Pow) and p.exp.is_number and p.exp.is_negative,
+                  lambda p: _INV(sp.Pow(p.base, -p.exp)))
+    return e
+
+
 def _pair_sincos(exprs):
     """sin(a) and cos(a) of the same argument -> one ``sincos`` call.  Returns the
     rewritten expressions and the list of paired arguments (already rewritten)."""
@@ -194,6 +225,10 @@ def print_body(printer: ModelPrinter, outputs: Sequence[Tuple[str, sp.MatrixBase
     else:
         common, reduced = [], []
 
+    if printer.dialect.name == "cuda":
+        common = [(sym, _strength_reduce(printer, e)) for sym, e in common]
+        reduced = [_strength_reduce(printer, e) for e in reduced]
+
     # definitions in dependency order: CSE temporaries and sincos pairs
     defs = {}
     for sym, expr in common:
@@ -203,7 +238,7 @@ def print_body(printer: ModelPrinter, outputs: Sequence[Tuple[str, sp.MatrixBase
     for k in range(len(pair_args)):
         arg = reduced[n_out + k]
         node = ([f"sn{k}", f"cs{k}"], {f.name for f in arg.free_symbols},
-                f"{indent}{real} sn{k}, cs{k}; sincos({_one_line(printer.doprint(arg))}, &sn{k}, &cs{k});")
+                f"{indent}{real} sn{k}, cs{k}; m_sincos({_one_line(printer.doprint(arg))}, &sn{k}, &cs{k});")
         defs[f"sn{k}"] = defs[f"cs{k}"] = node
     lines, done = [], set()
 

@@ -321,6 +321,12 @@ int32_t tplb_argmin_groups(const double* traj_costs, int32_t groups, int32_t per
     return check_launch("tplb_argmin_groups");
 }
 
+int32_t tplb_selftest_math(int32_t fn, const double* x, int32_t n, double* out, void* stream_) {
+    if (!x || !out || n <= 0 || fn < 0 || fn > 5) return fail(TPLB_E_ARG, "tplb_selftest_math: bad argument");
+    tplb::math_selftest_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream_)>>>(fn, x, n, out);
+    return check_launch("tplb_selftest_math");
+}
+
 double tplb_measure_fp64_tflops(int32_t repeats, void* stream_) {
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     int dev = 0, sms = 0;

@@ -5,10 +5,32 @@
 
 #include <cstdint>
 
+#include "fast_math.cuh"
+
 namespace tplb {
 
+// Elementary functions the generated code calls.  Default: the straight-line versions of
+// fast_math.cuh; -DTPLB_LIBDEVICE_MATH selects CUDA's libdevice for A/B comparisons.
+#ifdef TPLB_LIBDEVICE_MATH
+__device__ __forceinline__ double m_sin(double x) { return sin(x); }
+__device__ __forceinline__ double m_cos(double x) { return cos(x); }
+__device__ __forceinline__ double m_tan(double x) { return tan(x); }
+__device__ __forceinline__ void m_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+__device__ __forceinline__ double m_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ double m_rsqrt(double x) { return rsqrt(x); }
+__device__ __forceinline__ double m_inv(double x) { return 1.0 / x; }
+#else
+__device__ __forceinline__ double m_sin(double x) { return sin_bf(x); }
+__device__ __forceinline__ double m_cos(double x) { return cos_bf(x); }
+__device__ __forceinline__ double m_tan(double x) { return tan_bf(x); }
+__device__ __forceinline__ void m_sincos(double x, double* s, double* c) { sincos_bf(x, s, c); }
+__device__ __forceinline__ double m_sqrt(double x) { return sqrt_bf(x); }
+__device__ __forceinline__ double m_rsqrt(double x) { return rsqrt_bf(x); }
+__device__ __forceinline__ double m_inv(double x) { return inv_bf(x); }
+#endif
+
 template <typename R> __device__ __forceinline__ R sq(R a) { return a * a; }
-template <typename R> __device__ __forceinline__ R pow3h(R a) { return a * sqrt(a); }
+template <typename R> __device__ __forceinline__ R pow3h(R a) { return a * m_sqrt(a); }
 template <typename R> __device__ __forceinline__ R ipow3(R a) { return a * a * a; }
 template <typename R> __device__ __forceinline__ R ipow4(R a) { R b = a * a; return b * b; }
 template <typename R> __device__ __forceinline__ R ipow5(R a) { R b = a * a; return b * b * a; }

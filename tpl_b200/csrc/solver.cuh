@@ -295,7 +295,10 @@ rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int a_begin, 
         }
     };
 
-    // two stages per trip with ping-pong input buffers: no register copies between stages
+    // Two stages per trip with ping-pong input buffers (no register copies between stages);
+    // the loads of stage t+1 are issued before stage t is evaluated, so their latency hides
+    // behind the dynamics chain.  (Issuing them after the feedback law instead keeps fewer
+    // registers live but measured 17 % slower on B200.)
     Inputs in0, in1;
     fetch(0, in0);
     int t = 0;
@@ -1022,6 +1025,26 @@ __global__ void argmin_groups_kernel(const double* cost, int groups, int per_gro
         if (oa >= 0 && (ob < best || (ob == best && (arg < 0 || oa < arg)))) { best = ob; arg = oa; }
     }
     if (lane == 0) { min_cost[warp] = best; arg_min[warp] = arg; }
+}
+
+// ---------------------------------------------------------------------------------
+// self-test of the elementary functions the generated code uses (fast_math.cuh)
+// fn: 0 sin, 1 cos, 2 tan, 3 1/x, 4 1/sqrt(x), 5 sqrt(x)
+// ---------------------------------------------------------------------------------
+__global__ void math_selftest_kernel(int fn, const double* x, int n, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    double r = 0.0;
+    switch (fn) {
+        case 0: r = m_sin(v); break;
+        case 1: r = m_cos(v); break;
+        case 2: r = m_tan(v); break;
+        case 3: r = m_inv(v); break;
+        case 4: r = m_rsqrt(v); break;
+        default: r = m_sqrt(v); break;
+    }
+    out[i] = r;
 }
 
 // ---------------------------------------------------------------------------------
