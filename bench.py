@@ -366,11 +366,66 @@ def run_ours(a):
                 "value": cpu_v, "unit": UNIT, "cores": cores, "kind": kind,
                 "sample": f"first {used} problems of the same batch, one Optim object per problem, "
                           f"{cores} threads, update() only (GIL released)"}
+            # second half of the metric: p50 latency of ONE solve (batch = 1), same problem shape
+            line["latency"] = single_solve_latency(lib, pb, cpu=True)
+            # the same kernels once the batch fills the chip (not the headline workload)
+            line["large_batch"] = large_batch_throughput(lib, a, 65536)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line))
+
+
+def single_solve_latency(lib, pb, reps=200, cpu=True):
+    """p50 of one update() with batch = 1 (CUDA events around the call, parameters
+    resident), next to the reference's own `opt.runtime` for the same problem."""
+    import copy
+    import numpy as np
+    import torch
+    from tpl_b200 import scenarios as sc
+    from tpl_b200.batched import BatchedOptim
+    one = pb.subset([0])
+    opt = sc.apply_to_batched(BatchedOptim(lib, batch=1, horizon_max=one.horizon), one)
+    x0, u0 = opt._x[0].clone(), opt._u.clone()
+    times = []
+    for i in range(reps + 10):
+        opt._x[0].copy_(x0); opt._u.copy_(u0); opt.mu = 0.0; opt.mu_step = 0
+        torch.cuda.synchronize()
+        opt.update()
+        if i >= 10:
+            times.append(opt.runtime)
+    out = {"gpu_p50_ms": float(np.median(times)), "gpu_p90_ms": float(np.percentile(times, 90)),
+           "reps": reps, "what": "batch=1, one update() = 10 forced iterations, N=100, CUDA events around the call"}
+    if cpu:
+        factory, kind = cpu_solver_factory(pb.model)
+        base = sc.apply_to_single(factory(), pb, 0)
+        rt = []
+        for _ in range(50):
+            q = copy.deepcopy(base)
+            t0 = time.perf_counter()
+            q.update()
+            rt.append((time.perf_counter() - t0) * 1e3)
+        out["cpu_p50_ms"] = float(np.median(rt))
+        out["cpu_kind"] = kind
+    return out
+
+
+def large_batch_throughput(lib, a, batch):
+    import torch
+    from tpl_b200 import scenarios as sc
+    from tpl_b200.batched import BatchedOptim
+    pb = sc.mpc_time(batch=batch, horizon=a.horizon, max_iterations=a.iterations, forced=True)
+    opt = sc.apply_to_batched(BatchedOptim(lib, batch=batch, horizon_max=a.horizon), pb)
+    x0, u0 = opt._x[0].clone(), opt._u.clone()
+    best = None
+    for i in range(4):
+        opt._x[0].copy_(x0); opt._u.copy_(u0); opt.mu = 0.0; opt.mu_step = 0
+        torch.cuda.synchronize()
+        opt.update()
+        if i:
+            best = opt.runtime if best is None else min(best, opt.runtime)
+    return {"problems": batch, "value": batch / (best * 1e-3), "unit": UNIT, "ms_per_step": best}
 
 
 def main():

@@ -204,3 +204,111 @@ def test_fast_math_accuracy(solver_libs):
         _cabi.check(lib, lib.tplb_selftest_math(fn, x.data_ptr(), x.numel(), out.data_ptr(), stream), "selftest")
         err = _ulp_error(out.cpu().numpy(), ref(xs))
         assert err <= bound, f"fn {fn}: {err:.2f} ulp"
+
+
+def test_config3_multistart_sharded_by_scene(solver_libs, oracle_libs):
+    """BASELINE.json configs[2] at reduced size: scenes x multi-start warm starts with shared
+    parameters; per-scene argmin; a few problems checked against the CPU oracle."""
+    from tpl_b200 import scenarios as sc
+    scenes, per = 16, 64
+    pb = sc.mpc_time(batch=scenes * per, scenes=scenes, horizon=100, max_iterations=10, forced=False, seed0=500)
+    q = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
+    q.update()
+    mn, am = q.argmin_groups(per)
+    cost = q.traj_costs.cpu().numpy().reshape(scenes, per)
+    assert np.array_equal(mn.cpu().numpy(), cost.min(axis=1))
+    assert np.array_equal(am.cpu().numpy(), cost.argmin(axis=1) + np.arange(scenes) * per)
+    for i in (0, per + 3, scenes * per - 1):
+        o = sc.apply_to_single(oracle_libs.OracleOptim(pb.model), pb, i)
+        o.update()
+        assert int(q.iterations[i]) == int(o.iterations)
+        assert int(q.termination_condition[i]) == int(o.termination_condition)
+        assert common.rel_err(q.u[i].cpu().numpy(), np.asarray(o.u)) <= common.RTOL
+        assert abs(float(q.traj_costs[i]) - o.traj_costs) <= common.RTOL * abs(o.traj_costs)
+
+
+def test_config4_lateral_constraints_full_size(solver_libs, oracle_libs):
+    """BASELINE.json configs[3]: lateral profile with corridor constraints, N=200, batch 16384,
+    pure penalty and the augmented-Lagrangian variant: properties at full size + oracle samples."""
+    from tpl_b200 import scenarios as sc
+    for al in (False, True):
+        pb = sc.lateral(batch=16384, horizon=200, max_iterations=10, forced=False, seed0=7000,
+                        augmented_lagrangian=al)
+        q0 = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
+        r = copy.deepcopy(q0); r.max_iterations = 0; r.max_lg_iterations = 1; r.update()
+        q = copy.deepcopy(q0); q.update()
+        assert bool(torch.isfinite(q.traj_costs).all())
+        assert bool((q.u <= q.u_max).all()) and bool((q.u >= q.u_min).all())
+        assert bool((q.lg_iterations == pb.max_lg_iterations).all())
+        lam = q.lagrange_multiplier
+        assert bool((lam >= 0).all()) and bool((lam <= pb.lg_mult_limit).all())
+        if not al:
+            assert bool((q.traj_costs <= r.traj_costs).all())     # same multipliers: cost cannot increase
+            assert bool((lam == 0).all())
+        # the obstacle bump is respected up to the penalty's softness
+        d = q.x[:, :-1, 0]
+        lower = q.params.d_lower_constr
+        assert float((lower - d).max()) < 0.05
+        for i in (0, 8191, 16383):
+            o = sc.apply_to_single(oracle_libs.OracleOptim(pb.model), pb, i)
+            o.update()
+            assert int(q.iterations[i]) == int(o.iterations)
+            assert int(q.termination_condition[i]) == int(o.termination_condition)
+            assert common.rel_err(q.x[i].cpu().numpy(), np.asarray(o.x)) <= common.RTOL
+            assert abs(float(q.traj_costs[i]) - o.traj_costs) <= common.RTOL * abs(o.traj_costs)
+
+
+def test_config5_dead_time_compensation_then_solve(solver_libs, oracle_libs):
+    """BASELINE.json configs[4] in fp64: the MPC's dead-time roll-forward — 18 batched
+    `dynamics()` steps of 0.01 s with the steering / acceleration history
+    (control/model_predictive_controller_time.py:159-171) — followed by the solve with
+    ref_t_offset = 0.18, N=40, checked against the CPU oracle doing the same."""
+    from tpl_b200 import scenarios as sc
+    B, steps, cycle = 256, 18, 0.01
+    pb = sc.mpc_time(batch=B, horizon=40, max_iterations=20, forced=False, seed0=9000)
+    pb.scalars["ref_t_offset"][:] = steps * cycle
+    rng = np.random.default_rng(5)
+    hist_acc = rng.uniform(-1.0, 1.0, (steps, B))
+    hist_delta = rng.uniform(-0.05, 0.05, (steps, B))
+    q = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
+    x0 = torch.from_numpy(pb.x0).cuda()
+    zeros = torch.zeros(B, 2, dtype=torch.float64, device="cuda")
+    for s in range(steps):
+        x0[:, 3] = torch.from_numpy(hist_delta[s]).cuda()
+        x0[:, 5] = torch.from_numpy(hist_acc[s]).cuda()
+        x0 = q.dynamics(x0, zeros, 0, cycle).clone()
+    q.set_initial_state(x0)
+    q.update()
+    for i in (0, 100, 255):
+        o = sc.apply_to_single(oracle_libs.OracleOptim(pb.model), pb, i)
+        xo = pb.x0[i].copy()
+        for s in range(steps):
+            xo[3], xo[5] = hist_delta[s, i], hist_acc[s, i]
+            xo = o.dynamics(xo, np.zeros(2), 0, cycle)
+        assert common.rel_err(x0[i].cpu().numpy(), xo) < 1e-12
+        o.x[0] = xo
+        o.update()
+        assert int(q.iterations[i]) == int(o.iterations)
+        assert int(q.termination_condition[i]) == int(o.termination_condition)
+        assert common.rel_err(q.x[i].cpu().numpy(), np.asarray(o.x)) <= common.RTOL
+        assert common.rel_err(q.u[i].cpu().numpy(), np.asarray(o.u)) <= common.RTOL
+
+
+def test_forced_mode_flips_keep_the_solution(solver_libs, oracle_libs):
+    """Forced 10 iterations run the lateral model (converged after ~4) into the round-off
+    plateau, where the accept test compares costs that differ in the last bits and the decisions
+    (alpha, mu_step) become arbitrary — two CPU builds of the reference flip as well (SURVEY.md
+    finding 9).  The flip rate is reported; the solution must agree regardless."""
+    from tpl_b200 import scenarios as sc
+    pb = sc.lateral(batch=128, horizon=200, max_iterations=10, forced=True, seed0=100)
+    q = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
+    q.update()
+    flips = 0
+    for i in range(pb.batch):
+        o = sc.apply_to_single(oracle_libs.OracleOptim(pb.model), pb, i)
+        o.update()
+        same = int(q.mu_step[i]) == int(o.mu_step) and np.isclose(float(q.alpha[i]), o.alpha)
+        flips += 0 if same else 1
+        assert abs(float(q.traj_costs[i]) - o.traj_costs) <= 1e-9 * abs(o.traj_costs)
+        assert np.max(np.abs(q.x[i].cpu().numpy() - np.asarray(o.x))) <= 1e-6
+    print(f"forced-mode decision flips on the plateau: {flips}/{pb.batch}")
