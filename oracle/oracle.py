@@ -44,13 +44,13 @@ def build_libs():
     subprocess.run(["make", "-s", "-C", HERE], check=True)
 
 
-def _model_meta(name):
-    """scalar / array parameter names, parsed from the generated header's sibling
-    problem definition (kept in the package, the single source of truth)."""
+def _model_meta(name, cfg=None):
+    """scalar / array parameter names of a problem definition (the package's definitions
+    are the single source of truth for the names)."""
     import sys
     sys.path.insert(0, os.path.dirname(HERE))
     from tpl_b200 import optimizers, symext
-    cfg = optimizers.CONFIGS[name]()
+    cfg = cfg or optimizers.CONFIGS[name]()
     ps = cfg.param_symbols
     scal = [p.name for p in ps if not isinstance(p, symext.ArraySymbol)]
     arrs = [p.name for p in ps if isinstance(p, symext.ArraySymbol)]
@@ -58,6 +58,25 @@ def _model_meta(name):
 
 
 _META_CACHE = {}
+
+
+def build_custom(cfg, out_dir):
+    """Oracle library for a user-defined problem: generate its C routines and compile
+    ilqr_oracle.c against them.  Returns (name, library path)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
+    from tpl_b200 import codegen, derive
+    name = "custom_" + cfg.definition_hash()[:12]
+    os.makedirs(out_dir, exist_ok=True)
+    header = os.path.join(out_dir, name + ".h")
+    with open(header, "w") as fd:
+        fd.write(codegen.emit_c_model(derive.derive(cfg), name, cfg.definition_hash()))
+    lib = os.path.join(out_dir, f"liboracle_{name}.so")
+    subprocess.run(["gcc", "-O2", "-fno-fast-math", "-ffp-contract=off", "-fPIC", "-shared", "-w",
+                    f'-DTPLO_MODEL_HEADER="{header}"', os.path.join(HERE, "ilqr_oracle.c"),
+                    "-o", lib, "-lm"], check=True)
+    _META_CACHE[name] = _model_meta(name, cfg)
+    return name, lib
 
 
 class OracleParams:
@@ -95,11 +114,12 @@ class OracleParams:
 class OracleOptim:
     EULER, HEUN, RK4 = 0, 1, 2
 
-    def __init__(self, name):
-        path = os.path.join(HERE, "lib", f"liboracle_{name}.so")
+    def __init__(self, name, lib_path=None):
+        path = lib_path or os.path.join(HERE, "lib", f"liboracle_{name}.so")
         if not os.path.exists(path):
             build_libs()
         self._name = name
+        self._lib_path = lib_path
         self._lib = C.CDLL(path)
         dims = (C.c_int * 5)()
         size = self._lib.tplo_dims(dims)
@@ -212,7 +232,7 @@ class OracleOptim:
         return self._point(self._lib.tplo_ct_dynamics, x, u, t, dt)
 
     def __deepcopy__(self, memo):
-        o = OracleOptim(self._name)
+        o = OracleOptim(self._name, self._lib_path)
         for n, b in self._buf.items():
             o._buf[n][...] = b
         for f, _ in _Problem._fields_:

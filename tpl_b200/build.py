@@ -5,8 +5,10 @@ wrote ``optim.c`` and ran cmake.  Here the generated part is only the model
 header (``csrc/generated/<name>.cuh``); the solver kernels are the hand-written
 ``csrc/solver.cuh`` and the C ABI is ``csrc/cabi.cu``.
 
-The model zoo is built in-tree (``tpl_b200/lib/``) so the shared objects travel
-with the repository snapshot; other problems go to ``~/.cache/tpl_b200``.
+Everything is built in-tree so the shared objects travel with the repository
+snapshot: the model zoo into ``tpl_b200/lib/``, user-defined problems into
+``tpl_b200/lib/cache/<sha1>/`` (or ``$TPLB_CACHE_DIR``; the reference uses
+``~/.cache/genopt/<sha1>``, genopt.py:439).
 
     python -m tpl_b200.build            # build every zoo model that is stale
     python -m tpl_b200.build --regen    # regenerate the model headers too
@@ -76,7 +78,8 @@ def prepare_model_sources(config, name=None, lib_dir=None, regen=False) -> Prepa
         lib_dir = lib_dir or default_lib_dir()
     else:
         name = "genopt" + dh
-        root = os.path.expanduser(os.path.join("~/.cache/tpl_b200", dh))
+        cache = os.environ.get("TPLB_CACHE_DIR") or os.path.join(default_lib_dir(), "cache")
+        root = os.path.join(os.path.expanduser(cache), dh)
         header = os.path.join(root, name + ".cuh")
         lib_dir = lib_dir if (lib_dir and lib_dir != default_lib_dir()) else root
     os.makedirs(os.path.dirname(header), exist_ok=True)
