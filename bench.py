@@ -63,7 +63,11 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.marks = index, [], None, []
+
+    def mark(self):
+        """Bracket the timed region: samples outside [first mark, last mark + one period] are dropped."""
+        self.marks.append(time.time())
 
     def __enter__(self):
         try:
@@ -79,7 +83,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *exc):
         if self.proc:
@@ -90,7 +94,10 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        lo = self.marks[0] if self.marks else 0.0
+        hi = (self.marks[-1] + 0.05) if len(self.marks) > 1 else float("inf")
+        inside = [r for ts, r in self.rows if lo <= ts <= hi] or [r for _, r in self.rows[-3:]]
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -227,17 +234,21 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(a.warmup):
-        step()
-    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the sampler starts before the warm-up (nvidia-smi needs ~0.1 s to deliver its first
+    # line); only samples taken between the two barriers of the timed region are kept
     with ClockSampler(local) as clk:
+        for _ in range(a.warmup):
+            step()
         barrier()
+        clk.mark()
         e0.record()
         for _ in range(a.steps):
             step()
         e1.record()
         barrier()
+        clk.mark()
+        time.sleep(0.05)
     elapsed_ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
