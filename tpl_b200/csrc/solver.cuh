@@ -194,15 +194,11 @@ __device__ __forceinline__ void step_state(const PV& P, const R* x, const R* u, 
 //   kMinBlocks : 2 caps registers at 128 so two blocks fit per SM — more resident warps for
 //             batches that fill the chip; 1 keeps everything in registers for small batches
 // ---------------------------------------------------------------------------------
-template <typename M, int PB, bool kInit, int kScheme, int kMinBlocks>
-__global__ void __launch_bounds__(PB * (kInit ? 1 : kAlphas), kMinBlocks)
-rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int a_begin, const int32_t* list) {
+template <typename M, bool kInit, int kScheme>
+__device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace& ws, int b, int ai) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U, NSC = D::NSC;
-    const int ai = kInit ? 0 : a_begin + threadIdx.y;      // blockDim.y = candidates of this launch
     const int B = q.batch;
-    const int b = problem_of(list, ws.pending_count, blockIdx.x * PB + threadIdx.x, B);
-    if (b < 0) return;
     if (kInit) {
         ws.counters[b] = 0;
         ws.counters[(size_t)B + b] = 0;
@@ -284,14 +280,15 @@ rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int a_begin, 
         if (!kInit) {
             double* cut = cu + (size_t)t * U * B;
 #pragma unroll
-            for (int d = 0; d < U; ++d) cut[d * iB] = un[d];
+            for (int d = 0; d < U; ++d) __stcs(cut + d * iB, un[d]);       // streaming: keep K, k, x, u in L2
         }
         step_state<M, kScheme>(P, xn, un, cur.sc, (double)t, q.dt, xnext);
         double* cxt = cx + (size_t)(t + 1) * X * B;
 #pragma unroll
         for (int i = 0; i < X; ++i) {
             xn[i] = xnext[i];
-            cxt[i * iB] = xnext[i];
+            if (kInit) cxt[i * iB] = xnext[i];
+            else __stcs(cxt + i * iB, xnext[i]);
         }
     };
 
@@ -311,6 +308,15 @@ rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int a_begin, 
     if (t < T) stage(t, in0);
 }
 
+template <typename M, int PB, bool kInit, int kScheme, int kMinBlocks>
+__global__ void __launch_bounds__(PB * (kInit ? 1 : kAlphas), kMinBlocks)
+rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int a_begin, const int32_t* list) {
+    const int ai = kInit ? 0 : a_begin + threadIdx.y;      // blockDim.y = candidates of this launch
+    const int b = problem_of(list, ws.pending_count, blockIdx.x * PB + threadIdx.x, q.batch);
+    if (b < 0) return;
+    dev_rollout<M, kInit, kScheme>(q, ws, b, ai);
+}
+
 // ---------------------------------------------------------------------------------
 // cost terms of every (candidate, stage): stage cost for t < T, end cost for t == T.
 // grid (ceil(B/128), T+1, candidates of this launch).  Candidate a of problem b is read from
@@ -318,16 +324,12 @@ rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int a_begin, 
 // `list` != NULL: work items are entries of the pending list (round 2 of the line search).
 // ---------------------------------------------------------------------------------
 template <typename M>
-__global__ void stage_cost_kernel(const __grid_constant__ tplb_batch q, Workspace ws,
-                                  const double* xs, const double* us, size_t x_stride, size_t u_stride,
-                                  int check_running, int a_begin, const int32_t* list) {
+__device__ __forceinline__ void dev_stage_cost(const tplb_batch& q, const Workspace& ws,
+                                               const double* xs, const double* us, size_t x_stride,
+                                               size_t u_stride, int check_running, int b, int t, int a) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U, C = D::C;
-    const int t = blockIdx.y;
-    const int a = a_begin + blockIdx.z;
     const int B = q.batch;
-    const int b = problem_of(list, ws.pending_count, blockIdx.x * blockDim.x + threadIdx.x, B);
-    if (b < 0) return;
     if (check_running && !ws.running[b]) return;
     const int T = q.horizon;
     const int scene = __ldg(q.scene_index + b);
@@ -355,15 +357,28 @@ __global__ void stage_cost_kernel(const __grid_constant__ tplb_batch q, Workspac
     ws.cost_terms[((size_t)a * (q.t_max + 1) + t) * B + b] = c;
 }
 
+template <typename M>
+__global__ void stage_cost_kernel(const __grid_constant__ tplb_batch q, Workspace ws,
+                                  const double* xs, const double* us, size_t x_stride, size_t u_stride,
+                                  int check_running, int a_begin, const int32_t* list) {
+    const int b = problem_of(list, ws.pending_count, blockIdx.x * blockDim.x + threadIdx.x, q.batch);
+    if (b < 0) return;
+    dev_stage_cost<M>(q, ws, xs, us, x_stride, u_stride, check_running, b, blockIdx.y, a_begin + blockIdx.z);
+}
+
 // trajCosts of the initial rollout: sum in the reference's order (optim.c:1099-1111)
-__global__ void init_cost_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void dev_init_cost(const tplb_batch& q, const Workspace& ws, int b) {
     const int B = q.batch;
-    if (b >= B) return;
     double total = 0.0;
     const int T = q.horizon;
     for (int t = 0; t <= T; ++t) total += ws.cost_terms[(size_t)t * B + b];
     q.traj_costs[b] = total;
+}
+
+__global__ void init_cost_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= q.batch) return;
+    dev_init_cost(q, ws, b);
 }
 
 // ---------------------------------------------------------------------------------
@@ -371,13 +386,10 @@ __global__ void init_cost_kernel(const __grid_constant__ tplb_batch q, Workspace
 // the per-outer-iteration reset of the solver flags (row t == 0 does it).
 // ---------------------------------------------------------------------------------
 template <typename M>
-__global__ void multiplier_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
+__device__ __forceinline__ void dev_multiplier(const tplb_batch& q, const Workspace& ws, int b, int t) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U, C = D::C;
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = blockIdx.y;
     const int B = q.batch;
-    if (b >= B) return;
     if (t == 0) {
         q.trajectory_changed[b] = 1;
         q.improved[b] = 0;
@@ -409,6 +421,13 @@ __global__ void multiplier_kernel(const __grid_constant__ tplb_batch q, Workspac
     }
 }
 
+template <typename M>
+__global__ void multiplier_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= q.batch) return;
+    dev_multiplier<M>(q, ws, b, blockIdx.y);
+}
+
 // ---------------------------------------------------------------------------------
 // linearisation / quadratisation of every stage — thread per (problem, stage).
 // Only entries that are not identically 0/1 are stored (compact record).
@@ -417,14 +436,10 @@ __global__ void multiplier_kernel(const __grid_constant__ tplb_batch q, Workspac
 // line search accepted (the work of accept_kernel; grid has one extra row for x[T]).
 // ---------------------------------------------------------------------------------
 template <typename M, bool kForce, bool kAccept>
-__global__ void __launch_bounds__(128, 4)
-linearize_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
+__device__ __forceinline__ void dev_linearize(const tplb_batch& q, const Workspace& ws, int b, int t) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U, C = D::C;
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = blockIdx.y;                                // 0..T-1 (0..T with kAccept)
     const int B = q.batch;
-    if (b >= B) return;
     const int T = q.horizon;
 
     double x[X], u[U];
@@ -487,6 +502,14 @@ linearize_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
 #pragma unroll
     for (int e = 0; e < D::DENSE; ++e)
         if (M::deriv_owner(e)) out[(size_t)M::deriv_slot(e) * B] = blk[e];
+}
+
+template <typename M, bool kForce, bool kAccept>
+__global__ void __launch_bounds__(128, 4)
+linearize_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= q.batch) return;
+    dev_linearize<M, kForce, kAccept>(q, ws, b, blockIdx.y);   // rows 0..T-1 (0..T with kAccept)
 }
 
 // compact -> dense records for the fx..lux views (optim.c:1663-1669), thread per (problem, stage)
@@ -558,14 +581,10 @@ __device__ __forceinline__ void madd(double& acc, int slot, double a, double v) 
 // The next stage's compact record is prefetched while the current one is processed.
 // ---------------------------------------------------------------------------------
 template <typename M>
-__global__ void __launch_bounds__(128)
-backward_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteration) {
+__device__ __forceinline__ void dev_backward(const tplb_batch& q, const Workspace& ws, int b, int iteration) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U, NC = D::COMPACT;
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int B = q.batch;
-    if (b == 0) *ws.pending_count = 0;           // the line search of this iteration starts empty
-    if (b >= B) return;
     if (!ws.running[b]) return;
     q.iterations[b] = iteration + 1;             // optim.c:894
     ws.counters[b] += q.trajectory_changed[b] ? 1 : 0;
@@ -589,7 +608,7 @@ backward_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteratio
     auto fetch = [&](int t, double* r, double* uu, double* hh, double* ll) {
         const double* blk = ws.deriv + (size_t)t * NC * B + b;
 #pragma unroll
-        for (int s = 0; s < M::DERIV_COMPACT; ++s) r[s] = blk[(size_t)s * B];
+        for (int s = 0; s < M::DERIV_COMPACT; ++s) r[s] = __ldcs(blk + (size_t)s * B);   // read once
 #pragma unroll
         for (int d = 0; d < U; ++d) {
             const size_t idx = ((size_t)t * U + d) * B + b;
@@ -757,15 +776,22 @@ backward_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteratio
     }
 }
 
+template <typename M>
+__global__ void __launch_bounds__(128)
+backward_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteration) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) *ws.pending_count = 0;           // the line search of this iteration starts empty
+    if (b >= q.batch) return;
+    dev_backward<M>(q, ws, b, iteration);
+}
+
 // gradient-only sweep (optim.c:1038-1076): costate recursion, clipped descent direction
 template <typename M>
-__global__ void backward_first_order_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteration) {
+__device__ __forceinline__ void dev_backward_first_order(const tplb_batch& q, const Workspace& ws, int b,
+                                                         int iteration) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U;
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int B = q.batch;
-    if (b == 0) *ws.pending_count = 0;
-    if (b >= B) return;
     if (!ws.running[b]) return;
     q.iterations[b] = iteration + 1;
     ws.counters[b] += q.trajectory_changed[b] ? 1 : 0;
@@ -818,6 +844,14 @@ __global__ void backward_first_order_kernel(const __grid_constant__ tplb_batch q
     }
 }
 
+template <typename M>
+__global__ void backward_first_order_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteration) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) *ws.pending_count = 0;
+    if (b >= q.batch) return;
+    dev_backward_first_order<M>(q, ws, b, iteration);
+}
+
 // ---------------------------------------------------------------------------------
 // line-search decision in two rounds.  Costs are summed in the reference's
 // order (t = 0..T-1, then the end cost; optim.c:741-789); the lowest i whose cost
@@ -859,6 +893,40 @@ __device__ __forceinline__ void conclude_line_search(const tplb_batch& q, const 
     }
 }
 
+// cost of candidate a of problem b: the stage terms added in the reference's order
+__device__ __forceinline__ double dev_candidate_total(const tplb_batch& q, const Workspace& ws, int b, int a) {
+    const int B = q.batch, T = q.horizon;
+    const double* terms = ws.cost_terms + (size_t)a * (q.t_max + 1) * B + b;
+    double total = 0.0;
+    int t = 0;
+    for (; t + 8 <= T + 1; t += 8) {                         // loads in flight together, adds in order
+        double c[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = terms[(size_t)(t + j) * B];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) total += c[j];
+    }
+    for (; t <= T; ++t) total += terms[(size_t)t * B];
+    ws.cand_cost[(size_t)a * B + b] = total;
+    return total;
+}
+
+// lowest index in [a0, a0 + na) of s_total[.][lane] that passes testImprovement (optim.c:842)
+template <int PB>
+__device__ __forceinline__ int first_improving(const double (*s_total)[PB], int lane, int a0, int na,
+                                               double before, double& now) {
+    int win = -1;
+    now = before;
+    for (int i = na - 1; i >= 0; --i) {
+        const double c = s_total[i][lane];
+        if (c < before && isfinite(c) && c >= 0.0) {
+            win = a0 + i;
+            now = c;
+        }
+    }
+    return win;
+}
+
 // kRound == 1: block = PB problems x kRound1 candidates, every problem of the batch.
 // kRound == 2: block = PB pending problems x (8 - kRound1) candidates.
 template <int PB, int kRound>
@@ -871,22 +939,7 @@ select_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
     const int B = q.batch;
     const int b = problem_of(kRound == 1 ? nullptr : ws.pending, ws.pending_count, blockIdx.x * PB + lane, B);
     const bool live = b >= 0 && ws.running[b];
-    const int T = q.horizon;
-    double total = 0.0;
-    if (live) {
-        const double* terms = ws.cost_terms + (size_t)a * (q.t_max + 1) * B + b;
-        int t = 0;
-        for (; t + 8 <= T + 1; t += 8) {                     // loads in flight together, adds in order
-            double c[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) c[j] = terms[(size_t)(t + j) * B];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) total += c[j];
-        }
-        for (; t <= T; ++t) total += terms[(size_t)t * B];
-        ws.cand_cost[(size_t)a * B + b] = total;
-    }
-    s_total[threadIdx.y][lane] = total;
+    s_total[threadIdx.y][lane] = live ? dev_candidate_total(q, ws, b, a) : 0.0;
     __syncthreads();
     if (threadIdx.y != 0 || b < 0) return;
     if (!live) {                                             // stopped earlier: nothing to accept
@@ -894,16 +947,8 @@ select_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
         return;
     }
     const double before = q.traj_costs[b];
-    int win = -1;
-    double now = before;
-#pragma unroll
-    for (int i = NA - 1; i >= 0; --i) {
-        const double c = s_total[i][lane];
-        if (c < before && isfinite(c) && c >= 0.0) {         // testImprovement, optim.c:842
-            win = A0 + i;
-            now = c;
-        }
-    }
+    double now;
+    const int win = first_improving<PB>(s_total, lane, A0, NA, before, now);
     if (kRound == 1 && win < 0) {                            // alpha = 1 and 0.1 failed: try the rest
         ws.winner[b] = -1;
         ws.pending[atomicAdd(ws.pending_count, 1)] = b;
@@ -914,13 +959,10 @@ select_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
 
 // copy the accepted candidate into x, u (and keep prev_x, prev_k) — thread per (problem, stage)
 template <typename M>
-__global__ void accept_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
+__device__ __forceinline__ void dev_accept(const tplb_batch& q, const Workspace& ws, int b, int t) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U;
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = blockIdx.y;                                // 0..T
     const int B = q.batch;
-    if (b >= B) return;
     const int win = ws.winner[b];
     if (win < 0) return;
     const double* cx = ws.cand_x + (size_t)win * (q.t_max + 1) * X * B + b;
@@ -941,11 +983,137 @@ __global__ void accept_kernel(const __grid_constant__ tplb_batch q, Workspace ws
     }
 }
 
+template <typename M>
+__global__ void accept_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= q.batch) return;
+    dev_accept<M>(q, ws, b, blockIdx.y);                     // rows 0..T
+}
+
+__device__ __forceinline__ void dev_finalize(const tplb_batch& q, int b, int lg_done) {
+    q.lg_iterations[b] = lg_done;
+    if (q.iterations[b] == q.max_iterations) q.termination_condition[b] = 1;   // optim.c:1147-1149
+}
+
 __global__ void finalize_kernel(const __grid_constant__ tplb_batch q, int lg_done) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= q.batch) return;
-    q.lg_iterations[b] = lg_done;
-    if (q.iterations[b] == q.max_iterations) q.termination_condition[b] = 1;   // optim.c:1147-1149
+    dev_finalize(q, b, lg_done);
+}
+
+// ---------------------------------------------------------------------------------
+// The whole update() in ONE kernel for batches that cannot fill the chip.
+//
+// Problems are independent, so a block can take PB = 32 problems through every phase on
+// its own: the phases of the launch sequence above become sections of this kernel
+// separated by __syncthreads(), with exactly the same device functions doing the work.
+// Block = 32 problems (threadIdx.x, coalesced) x 8 warps (threadIdx.y):
+//   stage-parallel phases (linearise, cost terms, multipliers, accept): warp w takes stages
+//     w, w+8, ...;  rollouts: warp w is step size alpha_w;  chains per problem (initial
+//     rollout, Riccati sweep, ordered sums): warp 0 (or the warp of the candidate).
+// What it removes is everything between the kernels of the multi-launch path: ~75 launch
+// gaps and ramp-ups per update and the launch-latency-dominated small phases (select,
+// round-2 passes that find nothing to do).  Line-search round 2 uses a block-local pending
+// mask instead of the global list.  Results are identical to the multi-launch path.
+// ---------------------------------------------------------------------------------
+template <typename M, int kScheme>
+__global__ void __launch_bounds__(32 * kAlphas, 1)
+solve_block_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
+    using D = Dims<M>;
+    constexpr int PB = 32, NW = kAlphas, R2 = kAlphas - kRound1;
+    __shared__ double s_total[kAlphas][PB];
+    __shared__ int s_pending[PB];
+    const int lane = threadIdx.x, w = threadIdx.y;
+    const int B = q.batch, T = q.horizon;
+    const int b = blockIdx.x * PB + lane;
+    const bool valid = b < B;
+    const size_t cx_stride = (size_t)(q.t_max + 1) * D::X * B;
+    const size_t cu_stride = (size_t)q.t_max * D::U * B;
+
+    // initial rollout, its cost terms, trajCosts (optim.c:1096-1111)
+    if (w == 0 && valid) dev_rollout<M, true, kScheme>(q, ws, b, 0);
+    __syncthreads();
+    if (valid)
+        for (int t = w; t <= T; t += NW) dev_stage_cost<M>(q, ws, q.x, q.u, 0, 0, 0, b, t, 0);
+    __syncthreads();
+    if (w == 0 && valid) dev_init_cost(q, ws, b);
+    __syncthreads();
+
+    int lg = 0;
+    for (; lg < q.max_lg_iterations; ++lg) {
+        if (valid)
+            for (int t = w; t < (D::C > 0 ? T : 1); t += NW) dev_multiplier<M>(q, ws, b, t);
+        __syncthreads();
+
+        for (int s = 0; s < q.max_iterations; ++s) {
+            const bool run = valid && ws.running[b];
+            if (!__syncthreads_or(run)) break;               // every problem of this block has stopped
+
+            if (valid) {                                     // derivative records (+ accept of the last step)
+                if (s == 0) {
+                    for (int t = w; t < T; t += NW) dev_linearize<M, false, false>(q, ws, b, t);
+                } else {
+                    for (int t = w; t <= T; t += NW) dev_linearize<M, false, true>(q, ws, b, t);
+                }
+            }
+            __syncthreads();
+            if (w == 0 && valid) {                           // Riccati sweep
+                if (q.use_quadratic_terms) dev_backward<M>(q, ws, b, s);
+                else dev_backward_first_order<M>(q, ws, b, s);
+            }
+            __syncthreads();
+            if (valid) dev_rollout<M, false, kScheme>(q, ws, b, w);      // all 8 step sizes
+            __syncthreads();
+
+            // line search round 1: alpha = 1, 0.1
+            if (run)
+                for (int it = w; it < (T + 1) * kRound1; it += NW)
+                    dev_stage_cost<M>(q, ws, ws.cand_x, ws.cand_u, cx_stride, cu_stride, 0, b,
+                                      it % (T + 1), it / (T + 1));
+            __syncthreads();
+            if (w < kRound1) s_total[w][lane] = run ? dev_candidate_total(q, ws, b, w) : 0.0;
+            __syncthreads();
+            int pend = 0;
+            if (w == 0 && valid) {
+                if (!run) {
+                    ws.winner[b] = -1;                       // stopped earlier: nothing to accept
+                } else {
+                    const double before = q.traj_costs[b];
+                    double now;
+                    const int win = first_improving<PB>(s_total, lane, 0, kRound1, before, now);
+                    if (win < 0) {
+                        pend = 1;
+                        ws.winner[b] = -1;
+                    } else {
+                        conclude_line_search(q, ws, b, win, before, now);
+                    }
+                }
+            }
+            if (w == 0) s_pending[lane] = pend;
+            // round 2: alpha = 1e-2 .. 1e-7 for the problems of this block still pending
+            if (__syncthreads_or(pend)) {
+                const bool p = s_pending[lane] != 0;
+                if (p)
+                    for (int it = w; it < (T + 1) * R2; it += NW)
+                        dev_stage_cost<M>(q, ws, ws.cand_x, ws.cand_u, cx_stride, cu_stride, 0, b,
+                                          it % (T + 1), kRound1 + it / (T + 1));
+                __syncthreads();
+                if (w >= kRound1) s_total[w][lane] = p ? dev_candidate_total(q, ws, b, w) : 0.0;
+                __syncthreads();
+                if (w == 0 && p) {
+                    const double before = q.traj_costs[b];
+                    double now;
+                    const int win = first_improving<PB>(s_total + kRound1, lane, kRound1, R2, before, now);
+                    conclude_line_search(q, ws, b, win, before, now);
+                }
+                __syncthreads();
+            }
+        }
+        if (q.max_iterations > 0 && valid)                   // install the last accepted step
+            for (int t = w; t <= T; t += NW) dev_accept<M>(q, ws, b, t);
+        __syncthreads();
+    }
+    if (w == 0 && valid) dev_finalize(q, b, lg);
 }
 
 // ---------------------------------------------------------------------------------
