@@ -165,16 +165,27 @@ void launch_rollout(const tplb_batch& q, const tplb::Workspace& ws, cudaStream_t
                     int a_begin, int a_count, const int32_t* list) {
     const dim3 grid((q.batch + PB - 1) / PB), block(PB, kInit ? 1 : a_count);
     const bool dense = !kInit && q.batch >= 16384;         // enough blocks to want 2 per SM
-#define TPLB_ROLLOUT(SCHEME)                                                                            \
-    if (dense) tplb::rollout_kernel<Model, PB, kInit, SCHEME, kInit ? 1 : 2><<<grid, block, 0, st>>>(   \
-                   q, ws, a_begin, list);                                                               \
-    else tplb::rollout_kernel<Model, PB, kInit, SCHEME, 1><<<grid, block, 0, st>>>(q, ws, a_begin, list)
+    const size_t smem = sizeof(double) * 2 * tplb::RolloutInputs<Model, kInit>::COUNT * block.x * block.y;
+#define TPLB_ROLLOUT_K(SCHEME, MINB)                                                                  \
+    do {                                                                                              \
+        auto kern = tplb::rollout_kernel<Model, PB, kInit, SCHEME, MINB>;                             \
+        static bool configured = false;                                                               \
+        if (!configured) {                                                                            \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);      \
+            configured = true;                                                                        \
+        }                                                                                             \
+        kern<<<grid, block, smem, st>>>(q, ws, a_begin, list);                                        \
+    } while (0)
+#define TPLB_ROLLOUT(SCHEME)                              \
+    if (dense) TPLB_ROLLOUT_K(SCHEME, (kInit ? 1 : 2));   \
+    else TPLB_ROLLOUT_K(SCHEME, 1)
     switch (q.integrator_type) {
         case TPLB_EULER: TPLB_ROLLOUT(TPLB_EULER); break;
         case TPLB_HEUN: TPLB_ROLLOUT(TPLB_HEUN); break;
         default: TPLB_ROLLOUT(TPLB_RK4); break;
     }
 #undef TPLB_ROLLOUT
+#undef TPLB_ROLLOUT_K
 }
 
 // Rollouts in two rounds as well once the batch fills the chip: the 6 small step sizes are

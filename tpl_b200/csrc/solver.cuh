@@ -117,6 +117,16 @@ __device__ __forceinline__ ParamView<double> param_view_scene(const tplb_batch& 
     return P;
 }
 
+// 8-byte asynchronous copy global -> shared (LDGSTS).  Completion is tracked per thread by
+// commit / wait groups, not by the register scoreboard, so a consumer of the previous
+// batch never waits for the batch that was just issued.
+__device__ __forceinline__ void async_copy8(double* smem_dst, const double* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src));
+}
+__device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void async_wait_all_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
 template <typename M>
 __device__ __forceinline__ void load_stage_consts(const tplb_batch& q, const Workspace& ws, int scene, int t,
                                                   double* sc) {
@@ -193,10 +203,23 @@ __device__ __forceinline__ void step_state(const PV& P, const R* x, const R* u, 
 //             candidates go to ws.cand_x / ws.cand_u (the reference's next_x / next_u)
 //   kMinBlocks : 2 caps registers at 128 so two blocks fit per SM — more resident warps for
 //             batches that fill the chip; 1 keeps everything in registers for small batches
+// Dynamic shared memory: 2 * RolloutInputs::COUNT * threads doubles (input staging).
 // ---------------------------------------------------------------------------------
+// number of doubles one rollout stage reads per thread
+template <typename M, bool kInit>
+struct RolloutInputs {
+    static constexpr int X = M::X, U = M::U, NSC = M::NUM_STAGE_CONSTS;
+    static constexpr int O_U = 0, O_K = O_U + U, O_HI = O_K + (kInit ? 0 : U), O_LO = O_HI + (kInit ? 0 : U),
+                         O_KK = O_LO + (kInit ? 0 : U), O_X = O_KK + (kInit ? 0 : U * X),
+                         O_SC = O_X + (kInit ? 0 : X), COUNT = O_SC + NSC;
+};
+
+// `stage_in`: this block's staging area in shared memory, [2][COUNT][nt] doubles
 template <typename M, bool kInit, int kScheme>
-__device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace& ws, int b, int ai) {
+__device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace& ws, int b, int ai,
+                                            double* stage_in, int tid, int nt) {
     using D = Dims<M>;
+    using RI = RolloutInputs<M, kInit>;
     constexpr int X = D::X, U = D::U, NSC = D::NSC;
     const int B = q.batch;
     if (kInit) {
@@ -217,72 +240,79 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
 
     double* cx = kInit ? q.x + b : ws.cand_x + (size_t)ai * (q.t_max + 1) * X * B + b;
     double* cu = kInit ? nullptr : ws.cand_u + (size_t)ai * q.t_max * U * B + b;
-
-    // Everything stage t needs from memory, fetched one stage ahead so that the
-    // load latency overlaps the dynamics chain of the previous stage.
-    struct Inputs {
-        double u[U], k[U], hi[U], lo[U], K[U][X], xref[X], sc[D::NSCs];
-    };
     const int iB = B;                                        // component stride inside a stage
-    auto fetch = [&](int t, Inputs& in) {
-        const double* ut = q.u + (size_t)t * U * B + b;
+
+    // Everything stage t reads from global memory is copied asynchronously into this thread's
+    // column of the staging area one stage ahead (double buffered); the dynamics chain of stage
+    // t hides the latency of stage t+1.
+    auto slot = [&](int buf, int item) { return stage_in + ((size_t)buf * RI::COUNT + item) * nt + tid; };
+    auto fetch = [&](int t, int buf) {
+        const size_t su = (size_t)t * U * B + b;
 #pragma unroll
-        for (int d = 0; d < U; ++d) in.u[d] = __ldg(ut + d * iB);
-        if (!kInit) {
-            const double* kt = q.k + (size_t)t * U * B + b;
-            const double* ht = q.u_max + (size_t)t * U * B + b;
-            const double* lt = q.u_min + (size_t)t * U * B + b;
-#pragma unroll
-            for (int d = 0; d < U; ++d) {
-                in.k[d] = __ldg(kt + d * iB);
-                in.hi[d] = __ldg(ht + d * iB);
-                in.lo[d] = __ldg(lt + d * iB);
+        for (int d = 0; d < U; ++d) {
+            async_copy8(slot(buf, RI::O_U + d), q.u + su + d * iB);
+            if (!kInit) {
+                async_copy8(slot(buf, RI::O_K + d), q.k + su + d * iB);
+                async_copy8(slot(buf, RI::O_HI + d), q.u_max + su + d * iB);
+                async_copy8(slot(buf, RI::O_LO + d), q.u_min + su + d * iB);
             }
+        }
+        if (!kInit) {
             if (second_order) {
                 const double* Kt = q.K + (size_t)t * U * X * B + b;
 #pragma unroll
-                for (int d = 0; d < U; ++d)
-#pragma unroll
-                    for (int j = 0; j < X; ++j) in.K[d][j] = __ldg(Kt + (d * X + j) * iB);
+                for (int e = 0; e < U * X; ++e) async_copy8(slot(buf, RI::O_KK + e), Kt + e * iB);
             }
             const double* xt = q.x + (size_t)t * X * B + b;
 #pragma unroll
-            for (int j = 0; j < X; ++j) in.xref[j] = __ldg(xt + j * iB);
+            for (int j = 0; j < X; ++j) async_copy8(slot(buf, RI::O_X + j), xt + j * iB);
         }
         const double* st = ws.stage_consts + (size_t)t * NSC * q.scenes + scene;
 #pragma unroll
-        for (int j = 0; j < NSC; ++j) in.sc[j] = __ldg(st + j * q.scenes);
+        for (int j = 0; j < NSC; ++j) async_copy8(slot(buf, RI::O_SC + j), st + j * q.scenes);
     };
 
     double xn[X];
 #pragma unroll
     for (int i = 0; i < X; ++i) {
         xn[i] = q.x[(size_t)i * B + b];
-        if (!kInit) cx[(size_t)i * B] = xn[i];
+        if (!kInit) __stcs(cx + (size_t)i * B, xn[i]);
     }
 
-    auto stage = [&](int t, const Inputs& cur) {
-        double un[U], xnext[X];
+    fetch(0, 0);
+    async_commit();
+    for (int t = 0; t < T; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < T) fetch(t + 1, buf ^ 1);
+        async_commit();                                      // (possibly empty) group of stage t+1
+        async_wait_all_but_one();                            // stage t has landed
+
+        double un[U], xnext[X], sc[D::NSCs];
 #pragma unroll
         for (int d = 0; d < U; ++d) {
+            const double ud = *slot(buf, RI::O_U + d);
             if (kInit) {
-                un[d] = cur.u[d];
+                un[d] = ud;
             } else if (second_order) {
-                double v = cur.k[d] * alpha + cur.u[d];
+                double v = *slot(buf, RI::O_K + d) * alpha + ud;
 #pragma unroll
-                for (int j = 0; j < X; ++j) v += cur.K[d][j] * (xn[j] - cur.xref[j]);
-                const double capped = (cur.hi[d] < v) ? cur.hi[d] : v;     // optim.c:755-758
-                un[d] = (cur.lo[d] > capped) ? cur.lo[d] : capped;
+                for (int j = 0; j < X; ++j)
+                    v += *slot(buf, RI::O_KK + d * X + j) * (xn[j] - *slot(buf, RI::O_X + j));
+                const double hi = *slot(buf, RI::O_HI + d), lo = *slot(buf, RI::O_LO + d);
+                const double capped = (hi < v) ? hi : v;               // optim.c:755-758
+                un[d] = (lo > capped) ? lo : capped;
             } else {
-                un[d] = cur.u[d] - cur.k[d] * alpha;                       // optim.c:803-804
+                un[d] = ud - *slot(buf, RI::O_K + d) * alpha;          // optim.c:803-804
             }
         }
+#pragma unroll
+        for (int j = 0; j < NSC; ++j) sc[j] = *slot(buf, RI::O_SC + j);
         if (!kInit) {
             double* cut = cu + (size_t)t * U * B;
 #pragma unroll
-            for (int d = 0; d < U; ++d) __stcs(cut + d * iB, un[d]);       // streaming: keep K, k, x, u in L2
+            for (int d = 0; d < U; ++d) __stcs(cut + d * iB, un[d]);   // streaming: keep K, k, x, u in L2
         }
-        step_state<M, kScheme>(P, xn, un, cur.sc, (double)t, q.dt, xnext);
+        step_state<M, kScheme>(P, xn, un, sc, (double)t, q.dt, xnext);
         double* cxt = cx + (size_t)(t + 1) * X * B;
 #pragma unroll
         for (int i = 0; i < X; ++i) {
@@ -290,31 +320,18 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
             if (kInit) cxt[i * iB] = xnext[i];
             else __stcs(cxt + i * iB, xnext[i]);
         }
-    };
-
-    // Two stages per trip with ping-pong input buffers (no register copies between stages);
-    // the loads of stage t+1 are issued before stage t is evaluated, so their latency hides
-    // behind the dynamics chain.  (Issuing them after the feedback law instead keeps fewer
-    // registers live but measured 17 % slower on B200.)
-    Inputs in0, in1;
-    fetch(0, in0);
-    int t = 0;
-    for (; t + 1 < T; t += 2) {
-        fetch(t + 1, in1);
-        stage(t, in0);
-        if (t + 2 < T) fetch(t + 2, in0);
-        stage(t + 1, in1);
     }
-    if (t < T) stage(t, in0);
 }
 
 template <typename M, int PB, bool kInit, int kScheme, int kMinBlocks>
 __global__ void __launch_bounds__(PB * (kInit ? 1 : kAlphas), kMinBlocks)
 rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int a_begin, const int32_t* list) {
+    extern __shared__ double stage_in[];                   // [2][RolloutInputs::COUNT][threads]
     const int ai = kInit ? 0 : a_begin + threadIdx.y;      // blockDim.y = candidates of this launch
     const int b = problem_of(list, ws.pending_count, blockIdx.x * PB + threadIdx.x, q.batch);
     if (b < 0) return;
-    dev_rollout<M, kInit, kScheme>(q, ws, b, ai);
+    dev_rollout<M, kInit, kScheme>(q, ws, b, ai, stage_in, threadIdx.y * PB + threadIdx.x,
+                                   blockDim.x * blockDim.y);
 }
 
 // ---------------------------------------------------------------------------------
@@ -999,121 +1016,6 @@ __global__ void finalize_kernel(const __grid_constant__ tplb_batch q, int lg_don
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= q.batch) return;
     dev_finalize(q, b, lg_done);
-}
-
-// ---------------------------------------------------------------------------------
-// The whole update() in ONE kernel for batches that cannot fill the chip.
-//
-// Problems are independent, so a block can take PB = 32 problems through every phase on
-// its own: the phases of the launch sequence above become sections of this kernel
-// separated by __syncthreads(), with exactly the same device functions doing the work.
-// Block = 32 problems (threadIdx.x, coalesced) x 8 warps (threadIdx.y):
-//   stage-parallel phases (linearise, cost terms, multipliers, accept): warp w takes stages
-//     w, w+8, ...;  rollouts: warp w is step size alpha_w;  chains per problem (initial
-//     rollout, Riccati sweep, ordered sums): warp 0 (or the warp of the candidate).
-// What it removes is everything between the kernels of the multi-launch path: ~75 launch
-// gaps and ramp-ups per update and the launch-latency-dominated small phases (select,
-// round-2 passes that find nothing to do).  Line-search round 2 uses a block-local pending
-// mask instead of the global list.  Results are identical to the multi-launch path.
-// ---------------------------------------------------------------------------------
-template <typename M, int kScheme>
-__global__ void __launch_bounds__(32 * kAlphas, 1)
-solve_block_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
-    using D = Dims<M>;
-    constexpr int PB = 32, NW = kAlphas, R2 = kAlphas - kRound1;
-    __shared__ double s_total[kAlphas][PB];
-    __shared__ int s_pending[PB];
-    const int lane = threadIdx.x, w = threadIdx.y;
-    const int B = q.batch, T = q.horizon;
-    const int b = blockIdx.x * PB + lane;
-    const bool valid = b < B;
-    const size_t cx_stride = (size_t)(q.t_max + 1) * D::X * B;
-    const size_t cu_stride = (size_t)q.t_max * D::U * B;
-
-    // initial rollout, its cost terms, trajCosts (optim.c:1096-1111)
-    if (w == 0 && valid) dev_rollout<M, true, kScheme>(q, ws, b, 0);
-    __syncthreads();
-    if (valid)
-        for (int t = w; t <= T; t += NW) dev_stage_cost<M>(q, ws, q.x, q.u, 0, 0, 0, b, t, 0);
-    __syncthreads();
-    if (w == 0 && valid) dev_init_cost(q, ws, b);
-    __syncthreads();
-
-    int lg = 0;
-    for (; lg < q.max_lg_iterations; ++lg) {
-        if (valid)
-            for (int t = w; t < (D::C > 0 ? T : 1); t += NW) dev_multiplier<M>(q, ws, b, t);
-        __syncthreads();
-
-        for (int s = 0; s < q.max_iterations; ++s) {
-            const bool run = valid && ws.running[b];
-            if (!__syncthreads_or(run)) break;               // every problem of this block has stopped
-
-            if (valid) {                                     // derivative records (+ accept of the last step)
-                if (s == 0) {
-                    for (int t = w; t < T; t += NW) dev_linearize<M, false, false>(q, ws, b, t);
-                } else {
-                    for (int t = w; t <= T; t += NW) dev_linearize<M, false, true>(q, ws, b, t);
-                }
-            }
-            __syncthreads();
-            if (w == 0 && valid) {                           // Riccati sweep
-                if (q.use_quadratic_terms) dev_backward<M>(q, ws, b, s);
-                else dev_backward_first_order<M>(q, ws, b, s);
-            }
-            __syncthreads();
-            if (valid) dev_rollout<M, false, kScheme>(q, ws, b, w);      // all 8 step sizes
-            __syncthreads();
-
-            // line search round 1: alpha = 1, 0.1
-            if (run)
-                for (int it = w; it < (T + 1) * kRound1; it += NW)
-                    dev_stage_cost<M>(q, ws, ws.cand_x, ws.cand_u, cx_stride, cu_stride, 0, b,
-                                      it % (T + 1), it / (T + 1));
-            __syncthreads();
-            if (w < kRound1) s_total[w][lane] = run ? dev_candidate_total(q, ws, b, w) : 0.0;
-            __syncthreads();
-            int pend = 0;
-            if (w == 0 && valid) {
-                if (!run) {
-                    ws.winner[b] = -1;                       // stopped earlier: nothing to accept
-                } else {
-                    const double before = q.traj_costs[b];
-                    double now;
-                    const int win = first_improving<PB>(s_total, lane, 0, kRound1, before, now);
-                    if (win < 0) {
-                        pend = 1;
-                        ws.winner[b] = -1;
-                    } else {
-                        conclude_line_search(q, ws, b, win, before, now);
-                    }
-                }
-            }
-            if (w == 0) s_pending[lane] = pend;
-            // round 2: alpha = 1e-2 .. 1e-7 for the problems of this block still pending
-            if (__syncthreads_or(pend)) {
-                const bool p = s_pending[lane] != 0;
-                if (p)
-                    for (int it = w; it < (T + 1) * R2; it += NW)
-                        dev_stage_cost<M>(q, ws, ws.cand_x, ws.cand_u, cx_stride, cu_stride, 0, b,
-                                          it % (T + 1), kRound1 + it / (T + 1));
-                __syncthreads();
-                if (w >= kRound1) s_total[w][lane] = p ? dev_candidate_total(q, ws, b, w) : 0.0;
-                __syncthreads();
-                if (w == 0 && p) {
-                    const double before = q.traj_costs[b];
-                    double now;
-                    const int win = first_improving<PB>(s_total + kRound1, lane, kRound1, R2, before, now);
-                    conclude_line_search(q, ws, b, win, before, now);
-                }
-                __syncthreads();
-            }
-        }
-        if (q.max_iterations > 0 && valid)                   // install the last accepted step
-            for (int t = w; t <= T; t += NW) dev_accept<M>(q, ws, b, t);
-        __syncthreads();
-    }
-    if (w == 0 && valid) dev_finalize(q, b, lg);
 }
 
 // ---------------------------------------------------------------------------------
