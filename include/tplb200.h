@@ -24,7 +24,7 @@
  *  - layout is structure-of-arrays with the PROBLEM INDEX FASTEST: element
  *    (stage t, component i, problem b) of a trajectory lives at [(t*N + i)*batch + b].
  *    Shapes below are written slowest-to-fastest.
- *  - all reals are IEEE double; all integers int32.
+ *  - all reals are stored as IEEE double; all integers int32.
  *  - return value: 0 on success, TPLB_E_* (negative) for rejected arguments, or a
  *    positive cudaError_t from a failed launch.  tplb_last_error() describes it.
  */
@@ -50,6 +50,7 @@ extern "C" {
 #define TPLB_HORIZON_MAX 299              /* H_MAX - 1, optim.c:49, 1732 */
 
 enum { TPLB_EULER = 0, TPLB_HEUN = 1, TPLB_RK4 = 2 };           /* optim.c:492-496 */
+enum { TPLB_FP64 = 0, TPLB_FP32 = 1 };                          /* arithmetic of the kernels */
 enum {
     TPLB_E_ARG = -1,          /* null pointer / non-positive size */
     TPLB_E_HORIZON = -2,      /* horizon outside 1..t_max or t_max > TPLB_HORIZON_MAX */
@@ -92,7 +93,9 @@ typedef struct {
     int32_t integrator_type;       /* integratorType */
     int32_t use_quadratic_terms;   /* useQuadraticTerms: 1 = iLQR, 0 = gradient-only ilr */
     int32_t keep_previous;         /* 1: maintain prev_x / prev_k on accepted steps */
-    int32_t reserved0;
+    int32_t precision;             /* TPLB_FP64 (default, the reference's arithmetic) or TPLB_FP32:
+                                      kernels compute in fp32; storage, cost sums and the accept /
+                                      stop decisions stay fp64.  Needs locally centred coordinates. */
     double dt;                     /* dt ("step") */
     double min_rel_cost_change;    /* minRelCostChange */
 

@@ -40,3 +40,12 @@ for k, (ms, n) in prof.items():
     print(f"  {k:14s} {ms:8.3f} ms  {n:3d} launches  {ms/max(n,1)*1e3:8.1f} us/launch  {ms/tot:6.1%}")
 lin, bwd, roll = q0.work_counters()
 print("work per solve: lin %.2f bwd %.2f rollouts %.2f" % (lin.float().mean(), bwd.float().mean(), roll.float().mean()))
+if a.model == "mpc_time":
+    q0.precision = "fp32"
+    ts = []
+    for r in range(4):
+        q0._x.copy_(x0); q0._u.copy_(u0)
+        for k, v in st.items(): q0._status[k].copy_(v)
+        torch.cuda.synchronize(); q0.update(); ts.append(q0.runtime)
+    print(f"fp32 mode: {min(ts):.3f} ms -> {a.batch/min(ts)*1e3:.3e} solves/s")
+    q0.precision = "fp64"

@@ -130,7 +130,7 @@ class BatchedOptim:
     _STATUS = ("traj_costs", "alpha", "mu", "iterations", "lg_iterations", "mu_step",
                "trajectory_changed", "improved", "termination_condition")
     _SETTINGS = ("dt", "max_iterations", "max_lg_iterations", "min_rel_cost_change",
-                 "opt_start", "use_quadratic_terms", "integrator_type", "keep_previous")
+                 "opt_start", "use_quadratic_terms", "integrator_type", "keep_previous", "precision")
 
     def __init__(self, lib_path, batch=1, scenes=None, horizon_max=None, device=None):
         self._lib_path = lib_path
@@ -189,6 +189,7 @@ class BatchedOptim:
         self.opt_start = 0
         self.integrator_type = EULER
         self.keep_previous = True
+        self.precision = "fp64"            # "fp32": kernels compute in single precision
         self.params = BatchedParams(self)
 
     # -- settings -----------------------------------------------------------------
@@ -355,6 +356,7 @@ class BatchedOptim:
         q.integrator_type = int(self.integrator_type)
         q.use_quadratic_terms = int(bool(self.use_quadratic_terms))
         q.keep_previous = int(bool(self.keep_previous))
+        q.precision = {"fp64": 0, "fp32": 1}[self.precision]
         q.dt = float(self.dt)
         q.min_rel_cost_change = float(self.min_rel_cost_change)
         for name, t in (("x", self._x), ("u", self._u), ("prev_x", self._prev_x), ("prev_k", self._prev_k),

@@ -50,6 +50,8 @@ int validate(const tplb_batch* q) {
     if (q->opt_start != 0) return fail(TPLB_E_UNSUPPORTED, "opt_start != 0 is not supported");
     if (q->integrator_type < TPLB_EULER || q->integrator_type > TPLB_RK4)
         return fail(TPLB_E_UNSUPPORTED, "integrator_type must be EULER, HEUN or RK4");
+    if (q->precision != TPLB_FP64 && q->precision != TPLB_FP32)
+        return fail(TPLB_E_UNSUPPORTED, "precision must be TPLB_FP64 or TPLB_FP32");
     if (!q->x || !q->u || !q->k || !q->K || !q->u_min || !q->u_max || !q->traj_costs || !q->alpha ||
         !q->mu || !q->iterations || !q->lg_iterations || !q->mu_step || !q->trajectory_changed ||
         !q->improved || !q->termination_condition || !q->scene_index || !q->workspace)
@@ -160,7 +162,7 @@ namespace {
 constexpr int PB = 32;                                     // problems per rollout / select block
 // rollouts of candidates [a_begin, a_begin + a_count) for every problem (list == NULL) or
 // for the problems of the pending list
-template <bool kInit>
+template <typename R, bool kInit>
 void launch_rollout(const tplb_batch& q, const tplb::Workspace& ws, cudaStream_t st,
                     int a_begin, int a_count, const int32_t* list) {
     const dim3 grid((q.batch + PB - 1) / PB), block(PB, kInit ? 1 : a_count);
@@ -168,7 +170,7 @@ void launch_rollout(const tplb_batch& q, const tplb::Workspace& ws, cudaStream_t
     const size_t smem = sizeof(double) * 2 * tplb::RolloutInputs<Model, kInit>::COUNT * block.x * block.y;
 #define TPLB_ROLLOUT_K(SCHEME, MINB)                                                                  \
     do {                                                                                              \
-        auto kern = tplb::rollout_kernel<Model, PB, kInit, SCHEME, MINB>;                             \
+        auto kern = tplb::rollout_kernel<Model, R, PB, kInit, SCHEME, MINB>;                             \
         static bool configured = false;                                                               \
         if (!configured) {                                                                            \
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);      \
@@ -196,8 +198,19 @@ bool two_round_rollouts(int B) {
     return B >= 8192;
 }
 
+template <typename R>
+int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof);
+
+// precision 0: every kernel computes in fp64; 1: the kernels compute in fp32 (storage, cost
+// sums and all accept / stop decisions stay fp64)
 int run_update(const tplb_batch* qp, void* stream_, Profiler& prof) {
     if (int e = validate(qp)) return e;
+    return qp->precision == TPLB_FP32 ? run_update_as<float>(qp, stream_, prof)
+                                      : run_update_as<double>(qp, stream_, prof);
+}
+
+template <typename R>
+int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
     const tplb_batch q = *qp;
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     const tplb::Workspace ws = tplb::carve<Model>(q.workspace, q.batch, q.scenes, q.t_max);
@@ -216,35 +229,35 @@ int run_update(const tplb_batch* qp, void* stream_, Profiler& prof) {
     prof.after(TPLB_K_STAGE_CONSTS);
 
     prof.before();
-    launch_rollout<true>(q, ws, st, 0, 1, nullptr);
-    tplb::stage_cost_kernel<Model><<<dim3(sgx, T + 1, 1), sb, 0, st>>>(q, ws, q.x, q.u, 0, 0, 0, 0, nullptr);
+    launch_rollout<R, true>(q, ws, st, 0, 1, nullptr);
+    tplb::stage_cost_kernel<Model, R><<<dim3(sgx, T + 1, 1), sb, 0, st>>>(q, ws, q.x, q.u, 0, 0, 0, 0, nullptr);
     tplb::init_cost_kernel<<<sgx, sb, 0, st>>>(q, ws);
     prof.after(TPLB_K_ROLLOUT_INIT);
 
     int lg = 0;
     for (; lg < q.max_lg_iterations; ++lg) {
         prof.before();
-        tplb::multiplier_kernel<Model><<<dim3(sgx, Model::C > 0 ? T : 1), sb, 0, st>>>(q, ws);
+        tplb::multiplier_kernel<Model, R><<<dim3(sgx, Model::C > 0 ? T : 1), sb, 0, st>>>(q, ws);
         prof.after(TPLB_K_MULTIPLIER);
         for (int s = 0; s < q.max_iterations; ++s) {
             prof.before();
-            if (s == 0) tplb::linearize_kernel<Model, false, false><<<dim3(sgx, T), sb, 0, st>>>(q, ws);
-            else tplb::linearize_kernel<Model, false, true><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
+            if (s == 0) tplb::linearize_kernel<Model, R, false, false><<<dim3(sgx, T), sb, 0, st>>>(q, ws);
+            else tplb::linearize_kernel<Model, R, false, true><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
             prof.after(TPLB_K_LINEARIZE);
             prof.before();
             if (q.use_quadratic_terms)
-                tplb::backward_kernel<Model><<<pgrid, pb, 0, st>>>(q, ws, s);
+                tplb::backward_kernel<Model, R><<<pgrid, pb, 0, st>>>(q, ws, s);
             else
-                tplb::backward_first_order_kernel<Model><<<pgrid, pb, 0, st>>>(q, ws, s);
+                tplb::backward_first_order_kernel<Model, R><<<pgrid, pb, 0, st>>>(q, ws, s);
             prof.after(TPLB_K_BACKWARD);
 
             // round 1: alpha = 1, 0.1
             prof.before();
-            if (split_rollouts) launch_rollout<false>(q, ws, st, 0, R1, nullptr);
-            else launch_rollout<false>(q, ws, st, 0, tplb::kAlphas, nullptr);
+            if (split_rollouts) launch_rollout<R, false>(q, ws, st, 0, R1, nullptr);
+            else launch_rollout<R, false>(q, ws, st, 0, tplb::kAlphas, nullptr);
             prof.after(TPLB_K_ROLLOUT);
             prof.before();
-            tplb::stage_cost_kernel<Model><<<dim3(sgx, T + 1, R1), sb, 0, st>>>(
+            tplb::stage_cost_kernel<Model, R><<<dim3(sgx, T + 1, R1), sb, 0, st>>>(
                 q, ws, ws.cand_x, ws.cand_u, cx_stride, cu_stride, 1, 0, nullptr);
             prof.after(TPLB_K_STAGE_COST);
             prof.before();
@@ -254,11 +267,11 @@ int run_update(const tplb_batch* qp, void* stream_, Profiler& prof) {
             // round 2: alpha = 1e-2 .. 1e-7 for the problems still pending
             if (split_rollouts) {
                 prof.before();
-                launch_rollout<false>(q, ws, st, R1, R2, ws.pending);
+                launch_rollout<R, false>(q, ws, st, R1, R2, ws.pending);
                 prof.after(TPLB_K_ROLLOUT);
             }
             prof.before();
-            tplb::stage_cost_kernel<Model><<<dim3(sgx, T + 1, R2), sb, 0, st>>>(
+            tplb::stage_cost_kernel<Model, R><<<dim3(sgx, T + 1, R2), sb, 0, st>>>(
                 q, ws, ws.cand_x, ws.cand_u, cx_stride, cu_stride, 1, R1, ws.pending);
             prof.after(TPLB_K_STAGE_COST);
             prof.before();
@@ -299,7 +312,7 @@ int32_t tplb_linearize(const tplb_batch* qp, void* stream_) {
     const tplb::Workspace ws = tplb::carve<Model>(q.workspace, q.batch, q.scenes, q.t_max);
     const dim3 grid((q.batch + 127) / 128, q.horizon);
     tplb::stage_constants_kernel<Model><<<dim3((q.scenes + 127) / 128, q.horizon + 1), 128, 0, st>>>(q, ws);
-    tplb::linearize_kernel<Model, true, false><<<grid, 128, 0, st>>>(q, ws);
+    tplb::linearize_kernel<Model, double, true, false><<<grid, 128, 0, st>>>(q, ws);
     tplb::expand_derivatives_kernel<Model><<<grid, 128, 0, st>>>(q, ws, q.deriv_dense);
     return check_launch("tplb_linearize");
 }
@@ -317,8 +330,12 @@ int32_t tplb_dynamics(const tplb_batch* qp, const double* x_in, const double* u_
     if (!qp || !x_in || !u_in || !x_out || n <= 0) return fail(TPLB_E_ARG, "tplb_dynamics: bad argument");
     if (qp->struct_bytes != (int32_t)sizeof(tplb_batch)) return fail(TPLB_E_ABI, "tplb_batch size mismatch");
     const tplb_batch q = *qp;
-    tplb::dynamics_kernel<Model><<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream_)>>>(
-        q, x_in, u_in, scene_of_point, n, t, dt, continuous, x_out);
+    if (q.precision == TPLB_FP32)
+        tplb::dynamics_kernel<Model, float><<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream_)>>>(
+            q, x_in, u_in, scene_of_point, n, t, dt, continuous, x_out);
+    else
+        tplb::dynamics_kernel<Model, double><<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream_)>>>(
+            q, x_in, u_in, scene_of_point, n, t, dt, continuous, x_out);
     return check_launch("tplb_dynamics");
 }
 

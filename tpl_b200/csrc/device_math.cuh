@@ -28,6 +28,14 @@ __device__ __forceinline__ double m_sqrt(double x) { return sqrt_bf(x); }
 __device__ __forceinline__ double m_rsqrt(double x) { return rsqrt_bf(x); }
 __device__ __forceinline__ double m_inv(double x) { return inv_bf(x); }
 #endif
+// fp32 compute mode: libdevice's single-precision functions (<= 2 ulp, no slow path below 1e5)
+__device__ __forceinline__ float m_sin(float x) { return sinf(x); }
+__device__ __forceinline__ float m_cos(float x) { return cosf(x); }
+__device__ __forceinline__ float m_tan(float x) { return tanf(x); }
+__device__ __forceinline__ void m_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ float m_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ float m_rsqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ float m_inv(float x) { return 1.0f / x; }
 
 template <typename R> __device__ __forceinline__ R sq(R a) { return a * a; }
 template <typename R> __device__ __forceinline__ R pow3h(R a) { return a * m_sqrt(a); }
@@ -57,19 +65,20 @@ __device__ __forceinline__ R short_angle_dist(R from, R to) {
 }
 
 // Parameter view of ONE problem: scalars of its scene and its scene's rows of the
-// parameter arrays.  scalars: [num_scalars][S]; array a: [S][len[a]].
+// parameter arrays.  scalars: [num_scalars][S]; array a: [S][len[a]].  Storage is always
+// fp64; R is the type the model is evaluated in (double, or float in fp32 compute mode).
 template <typename R>
 struct ParamView {
-    const R* scalars;
-    const R* const* arrays;
+    const double* scalars;
+    const double* const* arrays;
     const int32_t* len;
     int32_t num_scenes;
     int32_t scene;
 
     __device__ __forceinline__ R scalar(int i) const {
-        return __ldg(scalars + (size_t)i * num_scenes + scene);
+        return R(__ldg(scalars + (size_t)i * num_scenes + scene));
     }
-    __device__ __forceinline__ const R* row(int a) const {
+    __device__ __forceinline__ const double* row(int a) const {
         return arrays[a] + (size_t)scene * len[a];
     }
 
@@ -83,8 +92,8 @@ struct ParamView {
         R w = q - R(lo);
         w = (R(0) > w) ? R(0) : w;
         w = (w < R(1)) ? w : R(1);
-        const R* p = row(a);
-        return (R(1) - w) * __ldg(p + lo) + w * __ldg(p + hi);
+        const double* p = row(a);
+        return (R(1) - w) * R(__ldg(p + lo)) + w * R(__ldg(p + hi));
     }
 
     // optim.c:392-406
@@ -97,16 +106,16 @@ struct ParamView {
         R w = q - R(lo);
         w = (R(0) > w) ? R(0) : w;
         w = (w < R(1)) ? w : R(1);
-        const R* p = row(a);
-        const R v0 = __ldg(p + lo);
-        return v0 + short_angle_dist(v0, __ldg(p + hi)) * w;
+        const double* p = row(a);
+        const R v0 = R(__ldg(p + lo));
+        return v0 + short_angle_dist(v0, R(__ldg(p + hi))) * w;
     }
 
     // optim.c:357-370
     __device__ __forceinline__ R box_interp(int a, R dx, R x) const {
         const int n = len[a];
         if (n == 0) return R(0);
-        return __ldg(row(a) + sample_index(floor(x / dx), n));
+        return R(__ldg(row(a) + sample_index(floor(x / dx), n)));
     }
 
     // optim.c:330 — the reference indexes unchecked; clamp instead of reading out of bounds
@@ -115,7 +124,7 @@ struct ParamView {
         if (n == 0) return R(0);
         int j = static_cast<int>(i);
         j = j < 0 ? 0 : (j >= n ? n - 1 : j);
-        return __ldg(row(a) + j);
+        return R(__ldg(row(a) + j));
     }
 };
 

@@ -107,8 +107,9 @@ __host__ __device__ inline Workspace carve(void* base, int B, int S, int t_max, 
     return w;
 }
 
-__device__ __forceinline__ ParamView<double> param_view_scene(const tplb_batch& q, int scene) {
-    ParamView<double> P;
+template <typename R>
+__device__ __forceinline__ ParamView<R> param_view_scene(const tplb_batch& q, int scene) {
+    ParamView<R> P;
     P.scalars = q.scalars;
     P.arrays = q.arrays;
     P.len = q.array_len;
@@ -127,12 +128,12 @@ __device__ __forceinline__ void async_copy8(double* smem_dst, const double* gmem
 __device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void async_wait_all_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
-template <typename M>
+template <typename M, typename R>
 __device__ __forceinline__ void load_stage_consts(const tplb_batch& q, const Workspace& ws, int scene, int t,
-                                                  double* sc) {
+                                                  R* sc) {
     constexpr int NSC = M::NUM_STAGE_CONSTS;
 #pragma unroll
-    for (int j = 0; j < NSC; ++j) sc[j] = __ldg(ws.stage_consts + ((size_t)t * NSC + j) * q.scenes + scene);
+    for (int j = 0; j < NSC; ++j) sc[j] = R(__ldg(ws.stage_consts + ((size_t)t * NSC + j) * q.scenes + scene));
 }
 
 // ---------------------------------------------------------------------------------
@@ -145,7 +146,7 @@ __global__ void stage_constants_kernel(const __grid_constant__ tplb_batch q, Wor
     const int t = blockIdx.y;                                   // 0..T
     if (s >= q.scenes) return;
     if (NSC == 0) return;
-    const ParamView<double> P = param_view_scene(q, s);
+    const ParamView<double> P = param_view_scene<double>(q, s);
     double sc[Dims<M>::NSCs];
     M::stage_constants(P, (double)t, q.dt, sc);
 #pragma unroll
@@ -215,7 +216,7 @@ struct RolloutInputs {
 };
 
 // `stage_in`: this block's staging area in shared memory, [2][COUNT][nt] doubles
-template <typename M, bool kInit, int kScheme>
+template <typename M, typename R, bool kInit, int kScheme>
 __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace& ws, int b, int ai,
                                             double* stage_in, int tid, int nt) {
     using D = Dims<M>;
@@ -231,12 +232,12 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
     }
     const int T = q.horizon;
     const int scene = __ldg(q.scene_index + b);
-    const ParamView<double> P = param_view_scene(q, scene);
+    const ParamView<R> P = param_view_scene<R>(q, scene);
     const bool second_order = q.use_quadratic_terms != 0;
 
     double tens = 1.0;
     for (int i = 0; i < ai; ++i) tens *= 10.0;
-    const double alpha = 1.0 / tens;
+    const R alpha = R(1.0 / tens);
 
     double* cx = kInit ? q.x + b : ws.cand_x + (size_t)ai * (q.t_max + 1) * X * B + b;
     double* cu = kInit ? nullptr : ws.cand_u + (size_t)ai * q.t_max * U * B + b;
@@ -272,11 +273,11 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
         for (int j = 0; j < NSC; ++j) async_copy8(slot(buf, RI::O_SC + j), st + j * q.scenes);
     };
 
-    double xn[X];
+    R xn[X];
 #pragma unroll
     for (int i = 0; i < X; ++i) {
-        xn[i] = q.x[(size_t)i * B + b];
-        if (!kInit) __stcs(cx + (size_t)i * B, xn[i]);
+        xn[i] = R(q.x[(size_t)i * B + b]);
+        if (!kInit) __stcs(cx + (size_t)i * B, (double)xn[i]);
     }
 
     fetch(0, 0);
@@ -287,50 +288,50 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
         async_commit();                                      // (possibly empty) group of stage t+1
         async_wait_all_but_one();                            // stage t has landed
 
-        double un[U], xnext[X], sc[D::NSCs];
+        R un[U], xnext[X], sc[D::NSCs];
 #pragma unroll
         for (int d = 0; d < U; ++d) {
-            const double ud = *slot(buf, RI::O_U + d);
+            const R ud = R(*slot(buf, RI::O_U + d));
             if (kInit) {
                 un[d] = ud;
             } else if (second_order) {
-                double v = *slot(buf, RI::O_K + d) * alpha + ud;
+                R v = R(*slot(buf, RI::O_K + d)) * alpha + ud;
 #pragma unroll
                 for (int j = 0; j < X; ++j)
-                    v += *slot(buf, RI::O_KK + d * X + j) * (xn[j] - *slot(buf, RI::O_X + j));
-                const double hi = *slot(buf, RI::O_HI + d), lo = *slot(buf, RI::O_LO + d);
-                const double capped = (hi < v) ? hi : v;               // optim.c:755-758
+                    v += R(*slot(buf, RI::O_KK + d * X + j)) * (xn[j] - R(*slot(buf, RI::O_X + j)));
+                const R hi = R(*slot(buf, RI::O_HI + d)), lo = R(*slot(buf, RI::O_LO + d));
+                const R capped = (hi < v) ? hi : v;               // optim.c:755-758
                 un[d] = (lo > capped) ? lo : capped;
             } else {
-                un[d] = ud - *slot(buf, RI::O_K + d) * alpha;          // optim.c:803-804
+                un[d] = ud - R(*slot(buf, RI::O_K + d)) * alpha;          // optim.c:803-804
             }
         }
 #pragma unroll
-        for (int j = 0; j < NSC; ++j) sc[j] = *slot(buf, RI::O_SC + j);
+        for (int j = 0; j < NSC; ++j) sc[j] = R(*slot(buf, RI::O_SC + j));
         if (!kInit) {
             double* cut = cu + (size_t)t * U * B;
 #pragma unroll
-            for (int d = 0; d < U; ++d) __stcs(cut + d * iB, un[d]);   // streaming: keep K, k, x, u in L2
+            for (int d = 0; d < U; ++d) __stcs(cut + d * iB, (double)un[d]);   // streaming: keep K, k, x, u in L2
         }
-        step_state<M, kScheme>(P, xn, un, sc, (double)t, q.dt, xnext);
+        step_state<M, kScheme>(P, xn, un, sc, R(t), R(q.dt), xnext);
         double* cxt = cx + (size_t)(t + 1) * X * B;
 #pragma unroll
         for (int i = 0; i < X; ++i) {
             xn[i] = xnext[i];
             if (kInit) cxt[i * iB] = xnext[i];
-            else __stcs(cxt + i * iB, xnext[i]);
+            else __stcs(cxt + i * iB, (double)xnext[i]);
         }
     }
 }
 
-template <typename M, int PB, bool kInit, int kScheme, int kMinBlocks>
+template <typename M, typename R, int PB, bool kInit, int kScheme, int kMinBlocks>
 __global__ void __launch_bounds__(PB * (kInit ? 1 : kAlphas), kMinBlocks)
 rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int a_begin, const int32_t* list) {
     extern __shared__ double stage_in[];                   // [2][RolloutInputs::COUNT][threads]
     const int ai = kInit ? 0 : a_begin + threadIdx.y;      // blockDim.y = candidates of this launch
     const int b = problem_of(list, ws.pending_count, blockIdx.x * PB + threadIdx.x, q.batch);
     if (b < 0) return;
-    dev_rollout<M, kInit, kScheme>(q, ws, b, ai, stage_in, threadIdx.y * PB + threadIdx.x,
+    dev_rollout<M, R, kInit, kScheme>(q, ws, b, ai, stage_in, threadIdx.y * PB + threadIdx.x,
                                    blockDim.x * blockDim.y);
 }
 
@@ -340,7 +341,7 @@ rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int a_begin, 
 // xs + a*x_stride, us + a*u_stride (the initial rollout passes q.x / q.u, 1 candidate).
 // `list` != NULL: work items are entries of the pending list (round 2 of the line search).
 // ---------------------------------------------------------------------------------
-template <typename M>
+template <typename M, typename R>
 __device__ __forceinline__ void dev_stage_cost(const tplb_batch& q, const Workspace& ws,
                                                const double* xs, const double* us, size_t x_stride,
                                                size_t u_stride, int check_running, int b, int t, int a) {
@@ -350,37 +351,37 @@ __device__ __forceinline__ void dev_stage_cost(const tplb_batch& q, const Worksp
     if (check_running && !ws.running[b]) return;
     const int T = q.horizon;
     const int scene = __ldg(q.scene_index + b);
-    const ParamView<double> P = param_view_scene(q, scene);
+    const ParamView<R> P = param_view_scene<R>(q, scene);
     const double* xa = xs + a * x_stride + b;
     const double* ua = us + a * u_stride + b;
 
-    double x[X], sc[D::NSCs], c;
+    R x[X], sc[D::NSCs], c;
 #pragma unroll
-    for (int i = 0; i < X; ++i) x[i] = xa[((size_t)t * X + i) * B];
-    load_stage_consts<M>(q, ws, scene, t, sc);
+    for (int i = 0; i < X; ++i) x[i] = R(xa[((size_t)t * X + i) * B]);
+    load_stage_consts<M, R>(q, ws, scene, t, sc);
     if (t < T) {
-        double u[U], lam[D::Cs], w[D::Cs];
+        R u[U], lam[D::Cs], w[D::Cs];
 #pragma unroll
-        for (int i = 0; i < U; ++i) u[i] = ua[((size_t)t * U + i) * B];
+        for (int i = 0; i < U; ++i) u[i] = R(ua[((size_t)t * U + i) * B]);
 #pragma unroll
         for (int cc = 0; cc < C; ++cc) {
-            lam[cc] = q.lagrange_multiplier[((size_t)t * C + cc) * B + b];
-            w[cc] = q.barrier_weight[(size_t)cc * B + b];
+            lam[cc] = R(q.lagrange_multiplier[((size_t)t * C + cc) * B + b]);
+            w[cc] = R(q.barrier_weight[(size_t)cc * B + b]);
         }
-        M::stage_cost(P, x, u, lam, w, sc, (double)t, q.dt, &c);
+        M::stage_cost(P, x, u, lam, w, sc, R(t), R(q.dt), &c);
     } else {
-        M::end_cost(P, x, sc, (double)T, q.dt, &c);
+        M::end_cost(P, x, sc, R(T), R(q.dt), &c);
     }
     ws.cost_terms[((size_t)a * (q.t_max + 1) + t) * B + b] = c;
 }
 
-template <typename M>
+template <typename M, typename R>
 __global__ void stage_cost_kernel(const __grid_constant__ tplb_batch q, Workspace ws,
                                   const double* xs, const double* us, size_t x_stride, size_t u_stride,
                                   int check_running, int a_begin, const int32_t* list) {
     const int b = problem_of(list, ws.pending_count, blockIdx.x * blockDim.x + threadIdx.x, q.batch);
     if (b < 0) return;
-    dev_stage_cost<M>(q, ws, xs, us, x_stride, u_stride, check_running, b, blockIdx.y, a_begin + blockIdx.z);
+    dev_stage_cost<M, R>(q, ws, xs, us, x_stride, u_stride, check_running, b, blockIdx.y, a_begin + blockIdx.z);
 }
 
 // trajCosts of the initial rollout: sum in the reference's order (optim.c:1099-1111)
@@ -402,7 +403,7 @@ __global__ void init_cost_kernel(const __grid_constant__ tplb_batch q, Workspace
 // multiplier update lambda <- min(limit, max(0, lambda + w g)) for every stage, and
 // the per-outer-iteration reset of the solver flags (row t == 0 does it).
 // ---------------------------------------------------------------------------------
-template <typename M>
+template <typename M, typename R>
 __device__ __forceinline__ void dev_multiplier(const tplb_batch& q, const Workspace& ws, int b, int t) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U, C = D::C;
@@ -415,34 +416,34 @@ __device__ __forceinline__ void dev_multiplier(const tplb_batch& q, const Worksp
     }
     if (C == 0) return;
     const int scene = __ldg(q.scene_index + b);
-    const ParamView<double> P = param_view_scene(q, scene);
-    double x[X], u[U], lam[D::Cs], w[D::Cs], g[D::Cs], sc[D::NSCs];
+    const ParamView<R> P = param_view_scene<R>(q, scene);
+    R x[X], u[U], lam[D::Cs], w[D::Cs], g[D::Cs], sc[D::NSCs];
 #pragma unroll
-    for (int i = 0; i < X; ++i) x[i] = q.x[((size_t)t * X + i) * B + b];
+    for (int i = 0; i < X; ++i) x[i] = R(q.x[((size_t)t * X + i) * B + b]);
 #pragma unroll
-    for (int i = 0; i < U; ++i) u[i] = q.u[((size_t)t * U + i) * B + b];
+    for (int i = 0; i < U; ++i) u[i] = R(q.u[((size_t)t * U + i) * B + b]);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        lam[c] = q.lagrange_multiplier[((size_t)t * C + c) * B + b];
-        w[c] = q.barrier_weight[(size_t)c * B + b];
-        g[c] = 0.0;
+        lam[c] = R(q.lagrange_multiplier[((size_t)t * C + c) * B + b]);
+        w[c] = R(q.barrier_weight[(size_t)c * B + b]);
+        g[c] = R(0);
     }
-    load_stage_consts<M>(q, ws, scene, t, sc);
-    M::constraints(P, x, u, lam, w, sc, (double)t, q.dt, g);
+    load_stage_consts<M, R>(q, ws, scene, t, sc);
+    M::constraints(P, x, u, lam, w, sc, R(t), R(q.dt), g);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        double v = lam[c] + w[c] * g[c];
-        v = (0.0 > v) ? 0.0 : v;
-        const double lim = q.lg_mult_limit[(size_t)c * B + b];
+        R v = lam[c] + w[c] * g[c];
+        v = (R(0) > v) ? R(0) : v;
+        const R lim = R(q.lg_mult_limit[(size_t)c * B + b]);
         q.lagrange_multiplier[((size_t)t * C + c) * B + b] = (lim < v) ? lim : v;
     }
 }
 
-template <typename M>
+template <typename M, typename R>
 __global__ void multiplier_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= q.batch) return;
-    dev_multiplier<M>(q, ws, b, blockIdx.y);
+    dev_multiplier<M, R>(q, ws, b, blockIdx.y);
 }
 
 // ---------------------------------------------------------------------------------
@@ -452,14 +453,14 @@ __global__ void multiplier_kernel(const __grid_constant__ tplb_batch q, Workspac
 // trajectory changed (optim.c:896).  kAccept: first install the step the previous
 // line search accepted (the work of accept_kernel; grid has one extra row for x[T]).
 // ---------------------------------------------------------------------------------
-template <typename M, bool kForce, bool kAccept>
+template <typename M, typename R, bool kForce, bool kAccept>
 __device__ __forceinline__ void dev_linearize(const tplb_batch& q, const Workspace& ws, int b, int t) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U, C = D::C;
     const int B = q.batch;
     const int T = q.horizon;
 
-    double x[X], u[U];
+    R x[X], u[U];
     bool have = false;
     if (kAccept) {
         // the step accepted by the previous line search becomes the trajectory (optim.c:844-848)
@@ -470,17 +471,19 @@ __device__ __forceinline__ void dev_linearize(const tplb_batch& q, const Workspa
 #pragma unroll
             for (int i = 0; i < X; ++i) {
                 const size_t idx = ((size_t)t * X + i) * B + b;
-                x[i] = cx[((size_t)t * X + i) * B];
+                const double xv = cx[((size_t)t * X + i) * B];
+                x[i] = R(xv);
                 if (q.keep_previous) q.prev_x[idx] = q.x[idx];
-                q.x[idx] = x[i];
+                q.x[idx] = xv;
             }
             if (t < T) {
 #pragma unroll
                 for (int d = 0; d < U; ++d) {
                     const size_t idx = ((size_t)t * U + d) * B + b;
-                    u[d] = cu[((size_t)t * U + d) * B];
+                    const double uv = cu[((size_t)t * U + d) * B];
+                    u[d] = R(uv);
                     if (q.keep_previous) q.prev_k[idx] = q.k[idx];
-                    q.u[idx] = u[d];
+                    q.u[idx] = uv;
                 }
             }
             have = true;
@@ -489,31 +492,31 @@ __device__ __forceinline__ void dev_linearize(const tplb_batch& q, const Workspa
     }
     if (!kForce && !(ws.running[b] && q.trajectory_changed[b])) return;
     const int scene = __ldg(q.scene_index + b);
-    const ParamView<double> P = param_view_scene(q, scene);
+    const ParamView<R> P = param_view_scene<R>(q, scene);
 
-    double lam[D::Cs], w[D::Cs], sc[D::NSCs];
+    R lam[D::Cs], w[D::Cs], sc[D::NSCs];
     if (!have) {
 #pragma unroll
-        for (int i = 0; i < X; ++i) x[i] = q.x[((size_t)t * X + i) * B + b];
+        for (int i = 0; i < X; ++i) x[i] = R(q.x[((size_t)t * X + i) * B + b]);
 #pragma unroll
-        for (int i = 0; i < U; ++i) u[i] = q.u[((size_t)t * U + i) * B + b];
+        for (int i = 0; i < U; ++i) u[i] = R(q.u[((size_t)t * U + i) * B + b]);
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        lam[c] = q.lagrange_multiplier[((size_t)t * C + c) * B + b];
-        w[c] = q.barrier_weight[(size_t)c * B + b];
+        lam[c] = R(q.lagrange_multiplier[((size_t)t * C + c) * B + b]);
+        w[c] = R(q.barrier_weight[(size_t)c * B + b]);
     }
-    load_stage_consts<M>(q, ws, scene, t, sc);
-    double blk[D::DENSE];
+    load_stage_consts<M, R>(q, ws, scene, t, sc);
+    R blk[D::DENSE];
     if (q.use_quadratic_terms) {
-        M::linearize(P, x, u, lam, w, sc, (double)t, q.dt,
+        M::linearize(P, x, u, lam, w, sc, R(t), R(q.dt),
                      blk + D::OFF_FX, blk + D::OFF_FU, blk + D::OFF_LX, blk + D::OFF_LU,
                      blk + D::OFF_LXX, blk + D::OFF_LUU, blk + D::OFF_LUX);
     } else {
 #pragma unroll
-        for (int e = D::OFF_LXX; e < D::DENSE; ++e) blk[e] = 0.0;
-        M::dynamics_jacobians(P, x, u, sc, (double)t, q.dt, blk + D::OFF_FX, blk + D::OFF_FU);
-        M::cost_gradients(P, x, u, lam, w, sc, (double)t, q.dt, blk + D::OFF_LX, blk + D::OFF_LU);
+        for (int e = D::OFF_LXX; e < D::DENSE; ++e) blk[e] = R(0);
+        M::dynamics_jacobians(P, x, u, sc, R(t), R(q.dt), blk + D::OFF_FX, blk + D::OFF_FU);
+        M::cost_gradients(P, x, u, lam, w, sc, R(t), R(q.dt), blk + D::OFF_LX, blk + D::OFF_LU);
     }
     double* out = ws.deriv + (size_t)t * D::COMPACT * B + b;
 #pragma unroll
@@ -521,12 +524,12 @@ __device__ __forceinline__ void dev_linearize(const tplb_batch& q, const Workspa
         if (M::deriv_owner(e)) out[(size_t)M::deriv_slot(e) * B] = blk[e];
 }
 
-template <typename M, bool kForce, bool kAccept>
+template <typename M, typename R, bool kForce, bool kAccept>
 __global__ void __launch_bounds__(128, 4)
 linearize_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= q.batch) return;
-    dev_linearize<M, kForce, kAccept>(q, ws, b, blockIdx.y);   // rows 0..T-1 (0..T with kAccept)
+    dev_linearize<M, R, kForce, kAccept>(q, ws, b, blockIdx.y);   // rows 0..T-1 (0..T with kAccept)
 }
 
 // compact -> dense records for the fx..lux views (optim.c:1663-1669), thread per (problem, stage)
@@ -549,35 +552,35 @@ __global__ void expand_derivatives_kernel(const __grid_constant__ tplb_batch q, 
 // ---------------------------------------------------------------------------------
 // gains  k = -(Quu + mu I)^-1 Qu,  K = -(Quu + mu I)^-1 Qux   (optim.c:243-291)
 // ---------------------------------------------------------------------------------
-template <int X, int U>
-__device__ __forceinline__ void control_gains(const double (&Quu)[U][U], const double (&Qu)[U],
-                                              const double (&Qux)[U][X], double mu,
-                                              double (&k)[U], double (&K)[U][X]) {
+template <int X, int U, typename R>
+__device__ __forceinline__ void control_gains(const R (&Quu)[U][U], const R (&Qu)[U],
+                                              const R (&Qux)[U][X], R mu,
+                                              R (&k)[U], R (&K)[U][X]) {
     static_assert(U == 1 || U == 2, "more than two controls are not supported (genopt.py:420-425)");
     if constexpr (U == 1) {
-        double s = 0.0;
-        if (Quu[0][0] > 0.0) s = -1.0 / (Quu[0][0] + mu);     // test on the un-regularised value
+        R s = R(0);
+        if (Quu[0][0] > R(0)) s = R(-1) / (Quu[0][0] + mu);     // test on the un-regularised value
         k[0] = Qu[0] * s;
 #pragma unroll
         for (int j = 0; j < X; ++j) K[0][j] = Qux[0][j] * s;
     } else {
-        const double a = Quu[0][0] + mu, bb = Quu[0][1], d = Quu[1][1] + mu;
-        const double det = a * d - bb * bb;
-        const double s = -1.0 / det;                          // no definiteness check
-        double Mi[2][2];
+        const R a = Quu[0][0] + mu, bb = Quu[0][1], d = Quu[1][1] + mu;
+        const R det = a * d - bb * bb;
+        const R s = R(-1) / det;                          // no definiteness check
+        R Mi[2][2];
         Mi[0][0] = d * s;
         Mi[0][1] = -bb * s;
         Mi[1][0] = Mi[0][1];
         Mi[1][1] = a * s;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            double acc = 0.0;
+            R acc = R(0);
 #pragma unroll
             for (int c = 0; c < 2; ++c) acc += Mi[i][c] * Qu[c];
             k[i] = acc;
 #pragma unroll
             for (int j = 0; j < X; ++j) {
-                double r = 0.0;
+                R r = R(0);
 #pragma unroll
                 for (int c = 0; c < 2; ++c) r += Mi[i][c] * Qux[c][j];
                 K[i][j] = r;
@@ -587,7 +590,8 @@ __device__ __forceinline__ void control_gains(const double (&Quu)[U][U], const d
 }
 
 // acc += a * v where `slot` is the compile-time structure of a: -1 -> a == 0, -2 -> a == 1
-__device__ __forceinline__ void madd(double& acc, int slot, double a, double v) {
+template <typename R>
+__device__ __forceinline__ void madd(R& acc, int slot, R a, R v) {
     if (slot == -1) return;
     if (slot == -2) acc += v;
     else acc += a * v;
@@ -597,7 +601,7 @@ __device__ __forceinline__ void madd(double& acc, int slot, double a, double v) 
 // backward Riccati sweep — thread per problem, value function in registers.
 // The next stage's compact record is prefetched while the current one is processed.
 // ---------------------------------------------------------------------------------
-template <typename M>
+template <typename M, typename R>
 __device__ __forceinline__ void dev_backward(const tplb_batch& q, const Workspace& ws, int b, int iteration) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U, NC = D::COMPACT;
@@ -608,30 +612,30 @@ __device__ __forceinline__ void dev_backward(const tplb_batch& q, const Workspac
     ws.counters[(size_t)B + b] += 1;
     q.trajectory_changed[b] = 0;                 // optim.c:911 (linearize_kernel ran just before)
     const int scene = __ldg(q.scene_index + b);
-    const ParamView<double> P = param_view_scene(q, scene);
+    const ParamView<R> P = param_view_scene<R>(q, scene);
     const int T = q.horizon;
     const double mu = q.mu[b];
 
-    double Vx[X], Vxx[X][X];
+    R Vx[X], Vxx[X][X];
     {
-        double xT[X], sc[D::NSCs];
+        R xT[X], sc[D::NSCs];
 #pragma unroll
-        for (int i = 0; i < X; ++i) xT[i] = q.x[((size_t)T * X + i) * B + b];
-        load_stage_consts<M>(q, ws, scene, T, sc);
-        M::end_derivatives(P, xT, sc, (double)T, q.dt, Vx, &Vxx[0][0]);
+        for (int i = 0; i < X; ++i) xT[i] = R(q.x[((size_t)T * X + i) * B + b]);
+        load_stage_consts<M, R>(q, ws, scene, T, sc);
+        M::end_derivatives(P, xT, sc, R(T), R(q.dt), Vx, &Vxx[0][0]);
     }
 
-    double rec[NC], nxt[NC], ub[U], hib[U], lob[U], nub[U], nhib[U], nlob[U];
-    auto fetch = [&](int t, double* r, double* uu, double* hh, double* ll) {
+    R rec[NC], nxt[NC], ub[U], hib[U], lob[U], nub[U], nhib[U], nlob[U];
+    auto fetch = [&](int t, R* r, R* uu, R* hh, R* ll) {
         const double* blk = ws.deriv + (size_t)t * NC * B + b;
 #pragma unroll
-        for (int s = 0; s < M::DERIV_COMPACT; ++s) r[s] = __ldcs(blk + (size_t)s * B);   // read once
+        for (int s = 0; s < M::DERIV_COMPACT; ++s) r[s] = R(__ldcs(blk + (size_t)s * B));   // read once
 #pragma unroll
         for (int d = 0; d < U; ++d) {
             const size_t idx = ((size_t)t * U + d) * B + b;
-            uu[d] = q.u[idx];
-            hh[d] = q.u_max[idx];
-            ll[d] = q.u_min[idx];
+            uu[d] = R(q.u[idx]);
+            hh[d] = R(q.u_max[idx]);
+            ll[d] = R(q.u_min[idx]);
         }
     };
     fetch(T - 1, nxt, nub, nhib, nlob);
@@ -646,26 +650,26 @@ __device__ __forceinline__ void dev_backward(const tplb_batch& q, const Workspac
         // dense entry e of the record: stored value, or the constant the structure says
         auto val = [&](int e) {
             const int s = M::deriv_slot(e);
-            return s >= 0 ? rec[s] : (s == -2 ? 1.0 : 0.0);
+            return s >= 0 ? rec[s] : (s == -2 ? R(1) : R(0));
         };
 #define A_(i, j) val(D::OFF_FX + (i) * X + (j))
 #define SA_(i, j) M::deriv_slot(D::OFF_FX + (i) * X + (j))
 #define B_(i, j) val(D::OFF_FU + (i) * U + (j))
 #define SB_(i, j) M::deriv_slot(D::OFF_FU + (i) * U + (j))
 
-        double Qx[X], Qu[U], Qxx[X][X], Quu[U][U], Qux[U][X];
-        double VA[X][X], VB[X][U];
+        R Qx[X], Qu[U], Qxx[X][X], Quu[U][U], Qux[U][X];
+        R VA[X][X], VB[X][U];
 
 #pragma unroll
         for (int i = 0; i < X; ++i) {                        // Qx = lx + A' Vx
-            double acc = 0.0;
+            R acc = R(0);
 #pragma unroll
             for (int r = 0; r < X; ++r) madd(acc, SA_(r, i), A_(r, i), Vx[r]);
             Qx[i] = val(D::OFF_LX + i) + acc;
         }
 #pragma unroll
         for (int i = 0; i < U; ++i) {                        // Qu = lu + B' Vx
-            double acc = 0.0;
+            R acc = R(0);
 #pragma unroll
             for (int r = 0; r < X; ++r) madd(acc, SB_(r, i), B_(r, i), Vx[r]);
             Qu[i] = val(D::OFF_LU + i) + acc;
@@ -674,14 +678,14 @@ __device__ __forceinline__ void dev_backward(const tplb_batch& q, const Workspac
         for (int i = 0; i < X; ++i) {                        // VA = Vxx A, VB = Vxx B
 #pragma unroll
             for (int j = 0; j < X; ++j) {
-                double acc = 0.0;
+                R acc = R(0);
 #pragma unroll
                 for (int r = 0; r < X; ++r) madd(acc, SA_(r, j), A_(r, j), Vxx[i][r]);
                 VA[i][j] = acc;
             }
 #pragma unroll
             for (int j = 0; j < U; ++j) {
-                double acc = 0.0;
+                R acc = R(0);
 #pragma unroll
                 for (int r = 0; r < X; ++r) madd(acc, SB_(r, j), B_(r, j), Vxx[i][r]);
                 VB[i][j] = acc;
@@ -691,7 +695,7 @@ __device__ __forceinline__ void dev_backward(const tplb_batch& q, const Workspac
         for (int i = 0; i < X; ++i)                          // Qxx = lxx + A' VA (lower triangle mirrored)
 #pragma unroll
             for (int j = 0; j <= i; ++j) {
-                double acc = 0.0;
+                R acc = R(0);
 #pragma unroll
                 for (int r = 0; r < X; ++r) madd(acc, SA_(r, i), A_(r, i), VA[r][j]);
                 Qxx[i][j] = acc;
@@ -705,7 +709,7 @@ __device__ __forceinline__ void dev_backward(const tplb_batch& q, const Workspac
         for (int i = 0; i < U; ++i)                          // Quu = luu + B' VB (lower triangle mirrored)
 #pragma unroll
             for (int j = 0; j <= i; ++j) {
-                double acc = 0.0;
+                R acc = R(0);
 #pragma unroll
                 for (int r = 0; r < X; ++r) madd(acc, SB_(r, i), B_(r, i), VB[r][j]);
                 Quu[i][j] = acc;
@@ -719,7 +723,7 @@ __device__ __forceinline__ void dev_backward(const tplb_batch& q, const Workspac
         for (int i = 0; i < U; ++i)                          // Qux = lux + B' VA
 #pragma unroll
             for (int j = 0; j < X; ++j) {
-                double acc = 0.0;
+                R acc = R(0);
 #pragma unroll
                 for (int r = 0; r < X; ++r) madd(acc, SB_(r, i), B_(r, i), VA[r][j]);
                 Qux[i][j] = val(D::OFF_LUX + i * X + j) + acc;
@@ -729,22 +733,22 @@ __device__ __forceinline__ void dev_backward(const tplb_batch& q, const Workspac
 #undef B_
 #undef SB_
 
-        double k[U], K[U][X];
-        control_gains<X, U>(Quu, Qu, Qux, mu, k, K);
+        R k[U], K[U][X];
+        control_gains<X, U, R>(Quu, Qu, Qux, mu, k, K);
 
         // box limits on the feed-forward step (optim.c:950-963)
 #pragma unroll
         for (int d = 0; d < U; ++d) {
-            const double cand = ub[d] + k[d];
+            const R cand = ub[d] + k[d];
             if (cand > hib[d]) {
                 k[d] = hib[d] - ub[d];
 #pragma unroll
-                for (int j = 0; j < X; ++j) K[d][j] = 0.0;
+                for (int j = 0; j < X; ++j) K[d][j] = R(0);
             }
             if (cand < lob[d]) {
                 k[d] = lob[d] - ub[d];
 #pragma unroll
-                for (int j = 0; j < X; ++j) K[d][j] = 0.0;
+                for (int j = 0; j < X; ++j) K[d][j] = R(0);
             }
             q.k[((size_t)t * U + d) * B + b] = k[d];
 #pragma unroll
@@ -752,19 +756,19 @@ __device__ __forceinline__ void dev_backward(const tplb_batch& q, const Workspac
         }
 
         // value function (optim.c:965-984)
-        double KtQux[X][X], KtQuu[X][U];
+        R KtQux[X][X], KtQuu[X][U];
 #pragma unroll
         for (int i = 0; i < X; ++i) {
 #pragma unroll
             for (int j = 0; j < X; ++j) {
-                double acc = 0.0;
+                R acc = R(0);
 #pragma unroll
                 for (int c = 0; c < U; ++c) acc += K[c][i] * Qux[c][j];
                 KtQux[i][j] = acc;
             }
 #pragma unroll
             for (int j = 0; j < U; ++j) {
-                double acc = 0.0;
+                R acc = R(0);
 #pragma unroll
                 for (int c = 0; c < U; ++c) acc += K[c][i] * Quu[c][j];
                 KtQuu[i][j] = acc;
@@ -774,14 +778,14 @@ __device__ __forceinline__ void dev_backward(const tplb_batch& q, const Workspac
         for (int i = 0; i < X; ++i)
 #pragma unroll
             for (int j = 0; j < X; ++j) {
-                double v = KtQux[j][i] + KtQux[i][j];
+                R v = KtQux[j][i] + KtQux[i][j];
 #pragma unroll
                 for (int c = 0; c < U; ++c) v += KtQuu[i][c] * K[c][j];
                 Vxx[i][j] = v + Qxx[i][j];
             }
 #pragma unroll
         for (int i = 0; i < X; ++i) {
-            double v = 0.0;
+            R v = R(0);
 #pragma unroll
             for (int c = 0; c < U; ++c) v += KtQuu[i][c] * k[c];
 #pragma unroll
@@ -793,17 +797,17 @@ __device__ __forceinline__ void dev_backward(const tplb_batch& q, const Workspac
     }
 }
 
-template <typename M>
+template <typename M, typename R>
 __global__ void __launch_bounds__(128)
 backward_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteration) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b == 0) *ws.pending_count = 0;           // the line search of this iteration starts empty
     if (b >= q.batch) return;
-    dev_backward<M>(q, ws, b, iteration);
+    dev_backward<M, R>(q, ws, b, iteration);
 }
 
 // gradient-only sweep (optim.c:1038-1076): costate recursion, clipped descent direction
-template <typename M>
+template <typename M, typename R>
 __device__ __forceinline__ void dev_backward_first_order(const tplb_batch& q, const Workspace& ws, int b,
                                                          int iteration) {
     using D = Dims<M>;
@@ -815,26 +819,26 @@ __device__ __forceinline__ void dev_backward_first_order(const tplb_batch& q, co
     ws.counters[(size_t)B + b] += 1;
     q.trajectory_changed[b] = 0;
     const int scene = __ldg(q.scene_index + b);
-    const ParamView<double> P = param_view_scene(q, scene);
+    const ParamView<R> P = param_view_scene<R>(q, scene);
     const int T = q.horizon;
-    double Vx[X];
+    R Vx[X];
     {
-        double xT[X], Vxx[X * X], sc[D::NSCs];
+        R xT[X], Vxx[X * X], sc[D::NSCs];
 #pragma unroll
-        for (int i = 0; i < X; ++i) xT[i] = q.x[((size_t)T * X + i) * B + b];
-        load_stage_consts<M>(q, ws, scene, T, sc);
-        M::end_derivatives(P, xT, sc, (double)T, q.dt, Vx, Vxx);
+        for (int i = 0; i < X; ++i) xT[i] = R(q.x[((size_t)T * X + i) * B + b]);
+        load_stage_consts<M, R>(q, ws, scene, T, sc);
+        M::end_derivatives(P, xT, sc, R(T), R(q.dt), Vx, Vxx);
     }
     for (int t = T - 1; t >= 0; --t) {
         const double* blk = ws.deriv + (size_t)t * D::COMPACT * B + b;
         auto val = [&](int e) {
             const int s = M::deriv_slot(e);
-            return s >= 0 ? blk[(size_t)s * B] : (s == -2 ? 1.0 : 0.0);
+            return s >= 0 ? R(blk[(size_t)s * B]) : (s == -2 ? R(1) : R(0));
         };
-        double Qx[X];
+        R Qx[X];
 #pragma unroll
         for (int i = 0; i < X; ++i) {
-            double acc = 0.0;
+            R acc = R(0);
 #pragma unroll
             for (int r = 0; r < X; ++r)
                 madd(acc, M::deriv_slot(D::OFF_FX + r * X + i), val(D::OFF_FX + r * X + i), Vx[r]);
@@ -842,17 +846,17 @@ __device__ __forceinline__ void dev_backward_first_order(const tplb_batch& q, co
         }
 #pragma unroll
         for (int i = 0; i < U; ++i) {
-            double acc = 0.0;
+            R acc = R(0);
 #pragma unroll
             for (int r = 0; r < X; ++r)
                 madd(acc, M::deriv_slot(D::OFF_FU + r * U + i), val(D::OFF_FU + r * U + i), Vx[r]);
-            const double gq = val(D::OFF_LU + i) + acc;
+            const R gq = val(D::OFF_LU + i) + acc;
             const size_t idx = ((size_t)t * U + i) * B + b;
-            const double ui = q.u[idx];
-            double kk = gq;
-            const double cand = ui - gq;
-            if (cand > q.u_max[idx]) kk = ui - q.u_max[idx];
-            if (cand < q.u_min[idx]) kk = ui - q.u_min[idx];
+            const R ui = R(q.u[idx]);
+            R kk = gq;
+            const R cand = ui - gq;
+            if (cand > R(q.u_max[idx])) kk = ui - R(q.u_max[idx]);
+            if (cand < R(q.u_min[idx])) kk = ui - R(q.u_min[idx]);
             if (q.g) q.g[idx] = gq;
             q.k[idx] = kk;
         }
@@ -861,12 +865,12 @@ __device__ __forceinline__ void dev_backward_first_order(const tplb_batch& q, co
     }
 }
 
-template <typename M>
+template <typename M, typename R>
 __global__ void backward_first_order_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteration) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b == 0) *ws.pending_count = 0;
     if (b >= q.batch) return;
-    dev_backward_first_order<M>(q, ws, b, iteration);
+    dev_backward_first_order<M, R>(q, ws, b, iteration);
 }
 
 // ---------------------------------------------------------------------------------
@@ -1051,7 +1055,7 @@ __global__ void shift_kernel(const __grid_constant__ tplb_batch q, int amount, c
 // point evaluations of the dynamics (optim.c:1512-1652); stage constants are
 // evaluated on the fly for the requested (t, dt)
 // ---------------------------------------------------------------------------------
-template <typename M>
+template <typename M, typename R>
 __global__ void dynamics_kernel(const __grid_constant__ tplb_batch q, const double* x_in, const double* u_in,
                                 const int32_t* scene_of_point, int n, int t, double dt, int continuous,
                                 double* x_out) {
@@ -1059,17 +1063,17 @@ __global__ void dynamics_kernel(const __grid_constant__ tplb_batch q, const doub
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int scene = scene_of_point ? scene_of_point[i] : ((n == q.batch && q.scene_index) ? q.scene_index[i] : 0);
-    const ParamView<double> P = param_view_scene(q, scene);
-    double x[X], u[U], out[X], sc[Dims<M>::NSCs];
+    const ParamView<R> P = param_view_scene<R>(q, scene);
+    R x[X], u[U], out[X], sc[Dims<M>::NSCs];
 #pragma unroll
-    for (int j = 0; j < X; ++j) x[j] = x_in[(size_t)j * n + i];
+    for (int j = 0; j < X; ++j) x[j] = R(x_in[(size_t)j * n + i]);
 #pragma unroll
-    for (int j = 0; j < U; ++j) u[j] = u_in[(size_t)j * n + i];
-    M::stage_constants(P, (double)t, dt, sc);
-    if (continuous) M::ct_dynamics(P, x, u, sc, (double)t, dt, out);
-    else if (q.integrator_type == TPLB_EULER) step_state<M, TPLB_EULER>(P, x, u, sc, (double)t, dt, out);
-    else if (q.integrator_type == TPLB_HEUN) step_state<M, TPLB_HEUN>(P, x, u, sc, (double)t, dt, out);
-    else step_state<M, TPLB_RK4>(P, x, u, sc, (double)t, dt, out);
+    for (int j = 0; j < U; ++j) u[j] = R(u_in[(size_t)j * n + i]);
+    M::stage_constants(P, R(t), R(dt), sc);
+    if (continuous) M::ct_dynamics(P, x, u, sc, R(t), R(dt), out);
+    else if (q.integrator_type == TPLB_EULER) step_state<M, TPLB_EULER>(P, x, u, sc, R(t), R(dt), out);
+    else if (q.integrator_type == TPLB_HEUN) step_state<M, TPLB_HEUN>(P, x, u, sc, R(t), R(dt), out);
+    else step_state<M, TPLB_RK4>(P, x, u, sc, R(t), R(dt), out);
 #pragma unroll
     for (int j = 0; j < X; ++j) x_out[(size_t)j * n + i] = out[j];
 }
