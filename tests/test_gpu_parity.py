@@ -406,3 +406,82 @@ def test_fp32_mode_against_fp64_oracle(solver_libs, oracle_libs):
     o = sc.apply_to_single(oracle_libs.OracleOptim(pb.model), pb, 5)
     o.update()
     assert common.rel_err(q64.x[5].cpu().numpy(), np.asarray(o.x)) <= common.RTOL
+
+
+def test_batch_isolation_and_nan_containment(solver_libs):
+    """Problems of a batch never influence each other: a sub-batch solved alone gives the
+    same bits as inside the big batch, and a problem with NaN parameters (its steps are all
+    rejected, optim.c:842) leaves its neighbours untouched."""
+    from tpl_b200 import scenarios as sc
+    pb = sc.mpc_time(batch=96, horizon=50, max_iterations=8, forced=False, seed0=600)
+    q = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
+    q.update()
+    idx = [3, 40, 41, 95]
+    sub = pb.subset(idx)
+    qs = sc.apply_to_batched(_factory(solver_libs, sub)(), sub)
+    qs.update()
+    assert torch.equal(qs.x, q.x[idx]) and torch.equal(qs.u, q.u[idx])
+    assert torch.equal(qs.traj_costs, q.traj_costs[idx]) and torch.equal(qs.iterations, q.iterations[idx])
+
+    bad = copy.deepcopy(pb)
+    bad.arrays = {k: v.copy() for k, v in pb.arrays.items()}
+    bad.arrays["ref_x"][7, 5:9] = np.nan
+    qb = sc.apply_to_batched(_factory(solver_libs, bad)(), bad)
+    qb.update()
+    keep = [i for i in range(pb.batch) if i != 7]
+    assert torch.equal(qb.x[keep], q.x[keep]) and torch.equal(qb.traj_costs[keep], q.traj_costs[keep])
+    assert not bool(torch.isfinite(qb.traj_costs[7]))                 # NaN cost is reported, not hidden
+    assert bool(torch.isfinite(qb.u[7]).all())                        # and no step was accepted on it
+
+
+@pytest.mark.parametrize("name,horizon,tol", [
+    ("ref_line_smoother_dk", 120, common.RTOL),
+    ("velocity_profile_time", 80, common.RTOL),
+])
+def test_remaining_zoo_models_against_oracle(name, horizon, tol, solver_libs, oracle_libs):
+    """The zoo models without a synthetic workload generator: random smooth inputs, CUDA vs CPU
+    oracle.  (The ill-conditioned 7x2 model is covered by the `mpc_strict` golden case on a
+    realistic path; random inputs make its finite-difference Hessians chaotic.)"""
+    from tpl_b200 import _cabi
+    from tpl_b200.batched import BatchedOptim
+    B = 8
+    rng = np.random.default_rng(11)
+    info = _cabi.model_info(_cabi.load(solver_libs[name]))
+    scal = {n: rng.uniform(0.5, 1.5) for n in info["scalar_names"]}
+    scal.update({k: v for k, v in dict(ref_step=0.5, s_start=0.0, l=3.0, v_ch=30.0, max_delta=0.6, max_acc=2.0,
+                                       min_acc=-3.0, a_offset=0.0, p_phi=50.0, pd=5.0).items() if k in scal})
+    arrs = {n: np.cumsum(rng.normal(0.0, 0.02, (B, 200)), axis=1) for n in info["array_names"]}
+    for n in arrs:
+        if n in ("ref_v", "ref_s_max"):
+            arrs[n] = 8.0 + arrs[n]
+        if n == "ref_x":
+            arrs[n] = np.arange(200)[None, :] * 0.5 + arrs[n]
+    x0 = rng.normal(0.0, 0.1, (B, info["X"]))
+    if name == "trajectory_tracking_mpc":
+        x0[:, 4] = 6.0; x0[:, 5] = 0.3
+    if name == "velocity_profile_time":
+        x0[:, 1] = 5.0
+    q = BatchedOptim(solver_libs[name], batch=B, horizon_max=horizon)
+
+    def configure(o, i=None):
+        o.horizon = horizon; o.step = 0.1 if name != "ref_line_smoother_dk" else 0.5
+        o.integrator_type = o.HEUN if name == "trajectory_tracking_mpc" else o.EULER
+        o.max_iterations = 6; o.min_rel_cost_change = 0.0
+        if info["C"]:
+            o.barrier_weight = 100.0; o.lg_mult_limit = 0.0
+        o.u_min = -1.0; o.u_max = 1.0
+        for n, v in scal.items():
+            setattr(o.params, n, v)
+        for n, v in arrs.items():
+            setattr(o.params, n, v if i is None else v[i])
+    configure(q)
+    q.set_initial_state(x0)
+    q.update()
+    for i in range(B):
+        o = oracle_libs.OracleOptim(name)
+        configure(o, i)
+        o.x[0] = x0[i]
+        o.update()
+        assert int(q.iterations[i]) == int(o.iterations)
+        assert common.rel_err(q.x[i].cpu().numpy(), np.asarray(o.x).reshape(horizon + 1, -1)) <= tol
+        assert abs(float(q.traj_costs[i]) - o.traj_costs) <= tol * abs(o.traj_costs)
