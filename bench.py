@@ -337,6 +337,15 @@ def run_ours(a):
                 hbm_peak = json.load(fd)["hbm_gbs"]
         except (OSError, KeyError, ValueError):
             hbm_peak = 6650.0
+        # DRAM bytes and FP64-pipe activity of the hot kernels from the committed ncu capture
+        # (profiles/ncu_traffic.json); only valid for the default workload
+        ncu = {}
+        try:
+            if (B, T) == (4096, 100):
+                with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fd:
+                    ncu = json.load(fd)["kernels"]
+        except (OSError, KeyError, ValueError):
+            ncu = {}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -355,7 +364,9 @@ def run_ours(a):
             "gpu_launches_per_step": launches,
             "roofline": {
                 "bound": "fp64", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                "frac": achieved / peak if peak > 0 else None,
+                "traffic": ncu.get(dom, {}).get("dram_bytes_per_launch"),
+                "fp64_pipe_active_pct_ncu": ncu.get(dom, {}).get("fp64_pipe_active_pct"),
                 "peak_source": "DFMA loop measured live by tplb_measure_fp64_tflops (MEASURED_PEAKS.json has no fp64 entry)",
                 "algorithmic_flops_per_launch": flops.get(dom, 0) / max(dom_n, 1),
                 "avg_launch_ms": dom_ms / max(dom_n, 1),

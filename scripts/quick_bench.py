@@ -16,7 +16,8 @@ a = ap.parse_args()
 t0 = time.time()
 pb = getattr(sc, a.model)(batch=a.batch, horizon=a.horizon, max_iterations=a.iters, forced=True)
 print(f"generated {a.batch} problems in {time.time()-t0:.1f}s")
-q0 = sc.apply_to_batched(BatchedOptim(build.zoo_library_path(pb.model), batch=pb.batch, horizon_max=pb.horizon), pb)
+libpath = os.environ.get("TPLB_LIB_OVERRIDE") or build.zoo_library_path(pb.model)
+q0 = sc.apply_to_batched(BatchedOptim(libpath, batch=pb.batch, horizon_max=pb.horizon), pb)
 print("fp64 peak TFLOP/s:", q0.measure_fp64_tflops())
 x0 = q0._x.clone(); u0 = q0._u.clone()
 st = {k: v.clone() for k, v in q0._status.items()}
