@@ -485,3 +485,22 @@ def test_remaining_zoo_models_against_oracle(name, horizon, tol, solver_libs, or
         assert int(q.iterations[i]) == int(o.iterations)
         assert common.rel_err(q.x[i].cpu().numpy(), np.asarray(o.x).reshape(horizon + 1, -1)) <= tol
         assert abs(float(q.traj_costs[i]) - o.traj_costs) <= tol * abs(o.traj_costs)
+
+
+def test_two_round_rollouts_are_bit_identical(solver_libs, monkeypatch):
+    """From 8192 problems per GPU on, the six small step sizes are rolled out only for the
+    problems whose alpha = 1 and 0.1 failed (pending list built with atomics).  Forcing that
+    path on a small batch must reproduce the single-round result bit for bit."""
+    from tpl_b200 import scenarios as sc
+    pb = sc.mpc_time(batch=200, horizon=60, max_iterations=10, forced=True, seed0=777)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("TPLB_TWO_ROUND_ROLLOUTS", mode)
+        q = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
+        q.update()
+        torch.cuda.synchronize()
+        out[mode] = (q.x.clone(), q.u.clone(), q.traj_costs.clone(), q.alpha.clone(), q.mu_step.clone())
+        rolled = q.work_counters()[2]
+        assert int(rolled.max()) > 10 + 1                       # some line searches went past alpha = 0.1
+    for a, b in zip(out["0"], out["1"]):
+        assert torch.equal(a, b)
