@@ -504,3 +504,40 @@ def test_two_round_rollouts_are_bit_identical(solver_libs, monkeypatch):
         assert int(rolled.max()) > 10 + 1                       # some line searches went past alpha = 0.1
     for a, b in zip(out["0"], out["1"]):
         assert torch.equal(a, b)
+
+
+def test_edge_shapes(solver_libs, oracle_libs):
+    """Shortest and longest horizons (optim.c:1726-1734: 1..299), a batch that is not a
+    multiple of the warp size, an EMPTY parameter array (lookups return 0.0, optim.c:363-365,
+    380-382) and a one-sample array."""
+    from tpl_b200 import scenarios as sc
+    for horizon, batch in ((1, 5), (2, 33), (299, 3)):
+        pb = sc.lateral(batch=batch, horizon=max(horizon, 2), max_iterations=4, forced=True, seed0=31)
+        pb.horizon = horizon
+        pb.u0, pb.u_min, pb.u_max = pb.u0[:, :horizon], pb.u_min[:, :horizon], pb.u_max[:, :horizon]
+        if horizon == 299:
+            pb = sc.lateral(batch=batch, horizon=299, max_iterations=4, forced=True, seed0=31)
+        q = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
+        q.update()
+        for i in range(batch):
+            o = sc.apply_to_single(oracle_libs.OracleOptim(pb.model), pb, i)
+            o.update()
+            assert int(q.iterations[i]) == int(o.iterations)
+            assert common.rel_err(q.x[i].cpu().numpy(), np.asarray(o.x).reshape(horizon + 1, -1)) <= common.RTOL
+            assert abs(float(q.traj_costs[i]) - o.traj_costs) <= common.RTOL * max(abs(o.traj_costs), 1e-300)
+
+    # empty and single-sample parameter arrays
+    pb = sc.lateral(batch=4, horizon=30, max_iterations=3, forced=True, seed0=5)
+    for variant in ("empty", "single"):
+        q = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
+        o = sc.apply_to_single(oracle_libs.OracleOptim(pb.model), pb, 2)
+        if variant == "empty":
+            q.params.k_ref = np.zeros((4, 0))
+            o.params.k_ref = np.zeros(0)
+        else:
+            q.params.k_ref = np.full((4, 1), 0.01)
+            o.params.k_ref = np.full(1, 0.01)
+        q.update()
+        o.update()
+        assert common.rel_err(q.x[2].cpu().numpy(), np.asarray(o.x)) <= common.RTOL
+        assert abs(float(q.traj_costs[2]) - o.traj_costs) <= common.RTOL * abs(o.traj_costs)
