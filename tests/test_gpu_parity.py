@@ -488,7 +488,7 @@ def test_remaining_zoo_models_against_oracle(name, horizon, tol, solver_libs, or
 
 
 def test_two_round_rollouts_are_bit_identical(solver_libs, monkeypatch):
-    """From 8192 problems per GPU on, the six small step sizes are rolled out only for the
+    """From 24576 problems per GPU on, the six small step sizes are rolled out only for the
     problems whose alpha = 1 and 0.1 failed (pending list built with atomics).  Forcing that
     path on a small batch must reproduce the single-round result bit for bit."""
     from tpl_b200 import scenarios as sc

@@ -195,7 +195,7 @@ void launch_rollout(const tplb_batch& q, const tplb::Workspace& ws, cudaStream_t
 // latency-bound and rolling out all 8 at once is free.
 bool two_round_rollouts(int B) {
     if (const char* e = std::getenv("TPLB_TWO_ROUND_ROLLOUTS")) return std::atoi(e) != 0;
-    return B >= 8192;
+    return B >= 24576;           // measured crossover on B200: 16384 -> single round, 32768 -> two rounds
 }
 
 template <typename R>
