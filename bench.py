@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--horizon", type=int, default=100)
     ap.add_argument("--iterations", type=int, default=10)
     ap.add_argument("--cpu-sample", type=int, default=2048)
+    ap.add_argument("--in-flight", type=int, default=4,
+                    help="batches in flight: solver instances (one CUDA stream each) the steps alternate between")
     return ap.parse_args()
 
 
@@ -210,24 +212,34 @@ def run_ours(a):
     if not os.path.exists(lib):
         build.build_zoo([MODEL])
     pb = sc.mpc_time(batch=B, horizon=T, max_iterations=I, forced=True, seed0=rank * B)
-    opt = sc.apply_to_batched(BatchedOptim(lib, batch=B, horizon_max=T), pb)
+    # `in_flight` solver instances, each on its own CUDA stream, take the batches round-robin
+    # (tpl_b200.streaming): one batch of 4096 leaves most SMs idle in the two serial phases, so
+    # consecutive batches overlap; with host buffers their copies overlap the kernels as well.
+    from tpl_b200.streaming import SolverPipeline
+    depth = max(1, a.in_flight)
+    pipe = SolverPipeline(lambda: sc.apply_to_batched(BatchedOptim(lib, batch=B, horizon_max=T), pb), depth=depth)
+    opt = pipe.slots[0].opt
     group = 64                                           # problems per argmin group (multi-start style)
 
     x0 = opt._x[0].clone()
     u0 = opt._u.clone()
+    torch.cuda.synchronize()                             # set-up ran on the default stream
 
-    def reset():
-        opt._x[0].copy_(x0)
-        opt._u.copy_(u0)
-        opt.mu = 0.0
-        opt.mu_step = 0
+    def reset(o=None):
+        o = opt if o is None else o
+        o._x[0].copy_(x0)
+        o._u.copy_(u0)
+        o.lagrange_multiplier = 0.0                      # a fresh problem, as in the reference arm
+        o.mu = 0.0
+        o.mu_step = 0
 
     def step():
-        reset()
-        opt.update()
-        if world > 1:
-            mn, am = opt.argmin_groups(group)
-            tdist.gather_best(mn, am, rank * B)
+        with pipe.next() as slot:
+            reset(slot.opt)
+            slot.opt.update()
+            if world > 1:
+                mn, am = slot.opt.argmin_groups(group)
+                tdist.gather_best(mn, am, rank * B)
 
     def barrier():
         if world > 1:
@@ -238,13 +250,16 @@ def run_ours(a):
     # the sampler starts before the warm-up (nvidia-smi needs ~0.1 s to deliver its first
     # line); only samples taken between the two barriers of the timed region are kept
     with ClockSampler(local) as clk:
-        for _ in range(a.warmup):
+        for _ in range(max(a.warmup, depth)):
             step()
+        pipe.join()
         barrier()
         clk.mark()
         e0.record()
+        pipe.fork()
         for _ in range(a.steps):
             step()
+        pipe.join()
         e1.record()
         barrier()
         clk.mark()
@@ -255,6 +270,7 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
     value = world * B * a.steps / (elapsed_ms * 1e-3)
+    resident_cost_check = float(opt.traj_costs.sum())
 
     # ---- end to end through the public API with host buffers --------------------------
     host = {
@@ -263,42 +279,58 @@ def run_ours(a):
         "arrays": {k: torch.from_numpy(v).pin_memory() for k, v in pb.arrays.items()},
         "scalars": {k: torch.from_numpy(v).pin_memory() for k, v in pb.scalars.items()},
     }
-    out_x = torch.empty((B, T + 1, opt.X), dtype=torch.float64).pin_memory()
-    out_u = torch.empty((B, T, opt.U), dtype=torch.float64).pin_memory()
-    out_c = torch.empty((B,), dtype=torch.float64).pin_memory()
-    out_i = torch.empty((2, B), dtype=torch.int32).pin_memory()
+    # same pipeline; every step uploads all of its inputs and downloads all of its results
+    # inside the timed region
+    outs = [{
+        "x": torch.empty((B, T + 1, opt.X), dtype=torch.float64).pin_memory(),
+        "u": torch.empty((B, T, opt.U), dtype=torch.float64).pin_memory(),
+        "c": torch.empty((B,), dtype=torch.float64).pin_memory(),
+        "i": torch.empty((2, B), dtype=torch.int32).pin_memory(),
+    } for _ in range(depth)]
     h2d = (host["x0"].numel() + host["u0"].numel()) * 8 + sum(v.numel() * 8 for v in host["arrays"].values()) \
         + sum(v.numel() * 8 for v in host["scalars"].values())
-    d2h = (out_x.numel() + out_u.numel() + out_c.numel()) * 8 + out_i.numel() * 4
+    d2h = (outs[0]["x"].numel() + outs[0]["u"].numel() + outs[0]["c"].numel()) * 8 + outs[0]["i"].numel() * 4
 
     def step_e2e():
-        for k, v in host["scalars"].items():
-            setattr(opt.params, k, v.to(dev, non_blocking=True))
-        for k, v in host["arrays"].items():
-            setattr(opt.params, k, v.to(dev, non_blocking=True))
-        opt.set_initial_state(host["x0"].to(dev, non_blocking=True))
-        opt.u = host["u0"].to(dev, non_blocking=True)
-        opt.mu = 0.0
-        opt.mu_step = 0
-        opt.update()
-        out_x.copy_(opt.x, non_blocking=True)
-        out_u.copy_(opt.u, non_blocking=True)
-        out_c.copy_(opt.traj_costs, non_blocking=True)
-        out_i[0].copy_(opt.iterations, non_blocking=True)
-        out_i[1].copy_(opt.termination_condition, non_blocking=True)
-        if world > 1:
-            mn, am = opt.argmin_groups(group)
-            tdist.gather_best(mn, am, rank * B)
+        with pipe.next() as slot:
+            o, out = slot.opt, outs[slot.index]
+            for k, v in host["scalars"].items():
+                setattr(o.params, k, v.to(dev, non_blocking=True))
+            for k, v in host["arrays"].items():
+                setattr(o.params, k, v.to(dev, non_blocking=True))
+            o.set_initial_state(host["x0"].to(dev, non_blocking=True))
+            o.u = host["u0"].to(dev, non_blocking=True)
+            o.lagrange_multiplier = 0.0
+            o.mu = 0.0
+            o.mu_step = 0
+            o.update()
+            out["x"].copy_(o.x, non_blocking=True)
+            out["u"].copy_(o.u, non_blocking=True)
+            out["c"].copy_(o.traj_costs, non_blocking=True)
+            out["i"][0].copy_(o.iterations, non_blocking=True)
+            out["i"][1].copy_(o.termination_condition, non_blocking=True)
+            if world > 1:
+                mn, am = o.argmin_groups(group)
+                tdist.gather_best(mn, am, rank * B)
 
-    for _ in range(max(1, a.warmup // 2)):
+    for _ in range(max(depth, a.warmup // 2)):
         step_e2e()
+    pipe.join()
     barrier()
     e0.record()
+    pipe.fork()
     for _ in range(a.steps):
         step_e2e()
+    pipe.join()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    # the downloaded results are the solver's: same costs as the device-resident run
+    pipe.slots[0].wait()
+    e2e_cost_check = float(outs[0]["c"].sum())
+    if abs(e2e_cost_check - resident_cost_check) > 1e-9 * abs(resident_cost_check):
+        raise SystemExit(f"end-to-end results differ from the device-resident run: "
+                         f"{e2e_cost_check!r} vs {resident_cost_check!r}")
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -353,13 +385,14 @@ def run_ours(a):
             "config": {
                 "workload": f"{B} independent {MODEL} problems per GPU (X=6,U=2,C=4), N={T}, "
                             f"{I} forced iLQR iterations, HEUN, fp64 (BASELINE.json configs[1])",
-                "problems_per_gpu": B, "stages": T, "iterations": I,
+                "problems_per_gpu": B, "stages": T, "iterations": I, "batches_in_flight": depth,
                 "flush": "working set per step (derivative blocks + 8 line-search candidates, "
                          f"{opt._workspace_bytes / 1e6:.0f} MB) exceeds the 126 MB L2; no explicit flush",
                 "final_collective": "all_gather of per-group (min cost, argmin)" if world > 1 else "none (1 GPU)",
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / a.steps},
+                    "ms_per_step": e2e_ms / a.steps, "batches_in_flight": depth,
+                    "cost_checksum": e2e_cost_check},
             "gpu_launches": launches * a.steps,
             "gpu_launches_per_step": launches,
             "roofline": {

@@ -541,3 +541,37 @@ def test_edge_shapes(solver_libs, oracle_libs):
         o.update()
         assert common.rel_err(q.x[2].cpu().numpy(), np.asarray(o.x)) <= common.RTOL
         assert abs(float(q.traj_costs[2]) - o.traj_costs) <= common.RTOL * abs(o.traj_costs)
+
+
+def test_batches_in_flight_are_independent(solver_libs):
+    """tpl_b200.streaming.SolverPipeline: several solver instances on their own CUDA streams
+    (what bench.py runs) give, batch by batch, exactly what one instance gives alone — with
+    host buffers, uploads and downloads enqueued on the slot's stream."""
+    from tpl_b200 import scenarios as sc
+    from tpl_b200.streaming import SolverPipeline
+    batches = [sc.mpc_time(batch=96, horizon=50, max_iterations=8, forced=True, seed0=1000 * i) for i in range(5)]
+    alone = []
+    for pb in batches:
+        q = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
+        q.update()
+        torch.cuda.synchronize()
+        alone.append((q.x.cpu(), q.u.cpu(), q.traj_costs.cpu()))
+
+    pipe = SolverPipeline(_factory(solver_libs, batches[0]), depth=3)
+    outs, slots = [], []
+    for pb in batches:
+        with pipe.next() as slot:
+            sc.apply_to_batched(slot.opt, pb)
+            slot.opt.mu, slot.opt.mu_step = 0.0, 0
+            slot.opt.update()
+            out = tuple(torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                        for t in (slot.opt.x, slot.opt.u, slot.opt.traj_costs))
+            for dst, src in zip(out, (slot.opt.x, slot.opt.u, slot.opt.traj_costs)):
+                dst.copy_(src, non_blocking=True)
+        outs.append(out)
+        slots.append(slot)
+    assert len({s.index for s in slots}) == 3
+    pipe.synchronize()
+    for got, want in zip(outs, alone):
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)

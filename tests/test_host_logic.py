@@ -137,3 +137,12 @@ def test_scenario_batches_are_seeded(solver_libs):
     assert sub.batch == 2 and np.array_equal(sub.x0[0], a.x0[5]) and sub.scenes == 2
     ms = sc.mpc_time(8, scenes=2, horizon=20)
     assert ms.scenes == 2 and ms.scene_of.tolist() == [0, 0, 0, 0, 1, 1, 1, 1]
+
+
+def test_pipeline_needs_cuda(lateral):
+    from tpl_b200.streaming import SolverPipeline
+    with pytest.raises(ValueError):
+        SolverPipeline(lambda: lateral, depth=0)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            SolverPipeline(lambda: lateral, depth=2)
