@@ -51,7 +51,9 @@ def parse():
     ap.add_argument("--horizon", type=int, default=100)
     ap.add_argument("--iterations", type=int, default=10)
     ap.add_argument("--cpu-sample", type=int, default=2048)
-    ap.add_argument("--in-flight", type=int, default=4,
+    ap.add_argument("--line-search-rounds", type=int, default=2, choices=[0, 1, 2],
+                    help="tplb_batch.line_search_rounds for the throughput legs (2: least work, for a full GPU)")
+    ap.add_argument("--in-flight", type=int, default=8,
                     help="batches in flight: solver instances (one CUDA stream each) the steps alternate between")
     return ap.parse_args()
 
@@ -229,7 +231,12 @@ def run_ours(a):
     # consecutive batches overlap; with host buffers their copies overlap the kernels as well.
     from tpl_b200.streaming import SolverPipeline
     depth = max(1, a.in_flight)
-    pipe = SolverPipeline(lambda: sc.apply_to_batched(BatchedOptim(lib, batch=B, horizon_max=T), pb), depth=depth)
+    def make_solver():
+        o = sc.apply_to_batched(BatchedOptim(lib, batch=B, horizon_max=T), pb)
+        o.line_search_rounds = a.line_search_rounds
+        return o
+
+    pipe = SolverPipeline(make_solver, depth=depth)
     opt = pipe.slots[0].opt
     group = 64                                           # problems per argmin group (multi-start style)
 
@@ -398,6 +405,7 @@ def run_ours(a):
                 "workload": f"{B} independent {MODEL} problems per GPU (X=6,U=2,C=4), N={T}, "
                             f"{I} forced iLQR iterations, HEUN, fp64 (BASELINE.json configs[1])",
                 "problems_per_gpu": B, "stages": T, "iterations": I, "batches_in_flight": depth,
+                "line_search_rounds": a.line_search_rounds,
                 "flush": "working set per step (derivative blocks + 8 line-search candidates, "
                          f"{opt._workspace_bytes / 1e6:.0f} MB) exceeds the 126 MB L2; no explicit flush",
                 "final_collective": "all_gather of per-group (min cost, argmin)" if world > 1 else "none (1 GPU)",

@@ -96,6 +96,14 @@ typedef struct {
     int32_t precision;             /* TPLB_FP64 (default, the reference's arithmetic) or TPLB_FP32:
                                       kernels compute in fp32; storage, cost sums and the accept /
                                       stop decisions stay fp64.  Needs locally centred coordinates. */
+    int32_t line_search_rounds;    /* how the 8 step sizes of optim.c:859-873 are rolled out; the accepted
+                                      step is the reference's in every mode (bit-identical results):
+                                      1 = all 8 at once (lowest latency of one batch),
+                                      2 = alpha = 1, 0.1 first, the other six only for the problems that
+                                          need them (least work: best when the GPU is full, i.e. large
+                                          batches or several batches in flight on different streams),
+                                      0 = choose by batch size (2 from 16384 problems on). */
+    int32_t reserved0;             /* must be 0 */
     double dt;                     /* dt ("step") */
     double min_rel_cost_change;    /* minRelCostChange */
 

@@ -487,23 +487,26 @@ def test_remaining_zoo_models_against_oracle(name, horizon, tol, solver_libs, or
         assert abs(float(q.traj_costs[i]) - o.traj_costs) <= tol * abs(o.traj_costs)
 
 
-def test_two_round_rollouts_are_bit_identical(solver_libs, monkeypatch):
-    """From 24576 problems per GPU on, the six small step sizes are rolled out only for the
-    problems whose alpha = 1 and 0.1 failed (pending list built with atomics).  Forcing that
-    path on a small batch must reproduce the single-round result bit for bit."""
-    from tpl_b200 import scenarios as sc
+def test_two_round_rollouts_are_bit_identical(solver_libs):
+    """`line_search_rounds` (tplb200.h): 1 rolls out all 8 step sizes at once, 2 rolls out the six
+    small ones only for the problems whose alpha = 1 and 0.1 failed (pending list built with
+    atomics; the automatic choice from 16384 problems on).  Same result bit for bit."""
+    from tpl_b200 import _cabi, scenarios as sc
     pb = sc.mpc_time(batch=200, horizon=60, max_iterations=10, forced=True, seed0=777)
     out = {}
-    for mode in ("0", "1"):
-        monkeypatch.setenv("TPLB_TWO_ROUND_ROLLOUTS", mode)
+    for rounds in (1, 2):
         q = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
+        q.line_search_rounds = rounds
         q.update()
         torch.cuda.synchronize()
-        out[mode] = (q.x.clone(), q.u.clone(), q.traj_costs.clone(), q.alpha.clone(), q.mu_step.clone())
+        out[rounds] = (q.x.clone(), q.u.clone(), q.traj_costs.clone(), q.alpha.clone(), q.mu_step.clone())
         rolled = q.work_counters()[2]
         assert int(rolled.max()) > 10 + 1                       # some line searches went past alpha = 0.1
-    for a, b in zip(out["0"], out["1"]):
+    for a, b in zip(out[1], out[2]):
         assert torch.equal(a, b)
+    q.line_search_rounds = 3
+    with pytest.raises(_cabi.SolverError):
+        q.update()
 
 
 def test_edge_shapes(solver_libs, oracle_libs):

@@ -130,7 +130,8 @@ class BatchedOptim:
     _STATUS = ("traj_costs", "alpha", "mu", "iterations", "lg_iterations", "mu_step",
                "trajectory_changed", "improved", "termination_condition")
     _SETTINGS = ("dt", "max_iterations", "max_lg_iterations", "min_rel_cost_change",
-                 "opt_start", "use_quadratic_terms", "integrator_type", "keep_previous", "precision")
+                 "opt_start", "use_quadratic_terms", "integrator_type", "keep_previous", "precision",
+                 "line_search_rounds")
 
     def __init__(self, lib_path, batch=1, scenes=None, horizon_max=None, device=None):
         self._lib_path = lib_path
@@ -190,6 +191,7 @@ class BatchedOptim:
         self.integrator_type = EULER
         self.keep_previous = True
         self.precision = "fp64"            # "fp32": kernels compute in single precision
+        self.line_search_rounds = 0        # 0 auto, 1 all step sizes at once, 2 in two rounds (tplb200.h)
         self.params = BatchedParams(self)
 
     # -- settings -----------------------------------------------------------------
@@ -357,6 +359,7 @@ class BatchedOptim:
         q.use_quadratic_terms = int(bool(self.use_quadratic_terms))
         q.keep_previous = int(bool(self.keep_previous))
         q.precision = {"fp64": 0, "fp32": 1}[self.precision]
+        q.line_search_rounds = int(self.line_search_rounds)
         q.dt = float(self.dt)
         q.min_rel_cost_change = float(self.min_rel_cost_change)
         for name, t in (("x", self._x), ("u", self._u), ("prev_x", self._prev_x), ("prev_k", self._prev_k),

@@ -52,6 +52,8 @@ int validate(const tplb_batch* q) {
         return fail(TPLB_E_UNSUPPORTED, "integrator_type must be EULER, HEUN or RK4");
     if (q->precision != TPLB_FP64 && q->precision != TPLB_FP32)
         return fail(TPLB_E_UNSUPPORTED, "precision must be TPLB_FP64 or TPLB_FP32");
+    if (q->line_search_rounds < 0 || q->line_search_rounds > 2 || q->reserved0 != 0)
+        return fail(TPLB_E_ARG, "line_search_rounds must be 0, 1 or 2");
     if (!q->x || !q->u || !q->k || !q->K || !q->u_min || !q->u_max || !q->traj_costs || !q->alpha ||
         !q->mu || !q->iterations || !q->lg_iterations || !q->mu_step || !q->trajectory_changed ||
         !q->improved || !q->termination_condition || !q->scene_index || !q->workspace)
@@ -167,7 +169,7 @@ void launch_rollout(const tplb_batch& q, const tplb::Workspace& ws, cudaStream_t
                     int a_begin, int a_count, const int32_t* list) {
     const dim3 grid((q.batch + PB - 1) / PB), block(PB, kInit ? 1 : a_count);
     const bool dense = !kInit && q.batch >= 16384;         // enough blocks to want 2 per SM
-    const size_t smem = sizeof(double) * 2 * tplb::RolloutInputs<Model, kInit>::COUNT * block.x * block.y;
+    const size_t smem = tplb::rollout_smem_bytes<Model, kInit>(PB);
 #define TPLB_ROLLOUT_K(SCHEME, MINB)                                                                  \
     do {                                                                                              \
         auto kern = tplb::rollout_kernel<Model, R, PB, kInit, SCHEME, MINB>;                             \
@@ -190,12 +192,14 @@ void launch_rollout(const tplb_batch& q, const tplb::Workspace& ws, cudaStream_t
 #undef TPLB_ROLLOUT_K
 }
 
-// Rollouts in two rounds as well once the batch fills the chip: the 6 small step sizes are
-// then rolled out only for the problems that need them.  Below that every phase is
-// latency-bound and rolling out all 8 at once is free.
-bool two_round_rollouts(int B) {
+// tplb_batch.line_search_rounds.  Auto: two rounds once the batch fills the chip — the six
+// small step sizes are then rolled out only for the problems that need them; below that
+// every phase is latency-bound and rolling out all 8 at once costs nothing.
+// (TPLB_TWO_ROUND_ROLLOUTS=0/1 overrides, for experiments.)
+bool two_round_rollouts(const tplb_batch& q) {
     if (const char* e = std::getenv("TPLB_TWO_ROUND_ROLLOUTS")) return std::atoi(e) != 0;
-    return B >= 24576;           // measured crossover on B200: 16384 -> single round, 32768 -> two rounds
+    if (q.line_search_rounds != 0) return q.line_search_rounds == 2;
+    return q.batch >= 16384;     // measured on B200: 8192 -> one round, 16384 -> two rounds
 }
 
 template <typename R>
@@ -222,7 +226,7 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
     const size_t cx_stride = (size_t)(q.t_max + 1) * Model::X * B;
     const size_t cu_stride = (size_t)q.t_max * Model::U * B;
     constexpr int R1 = tplb::kRound1, R2 = tplb::kAlphas - tplb::kRound1;
-    const bool split_rollouts = two_round_rollouts(B);
+    const bool split_rollouts = two_round_rollouts(q);
 
     prof.before();
     tplb::stage_constants_kernel<Model><<<dim3((S + sb - 1) / sb, T + 1), sb, 0, st>>>(q, ws);

@@ -204,7 +204,7 @@ __device__ __forceinline__ void step_state(const PV& P, const R* x, const R* u, 
 //             candidates go to ws.cand_x / ws.cand_u (the reference's next_x / next_u)
 //   kMinBlocks : 2 caps registers at 128 so two blocks fit per SM — more resident warps for
 //             batches that fill the chip; 1 keeps everything in registers for small batches
-// Dynamic shared memory: 2 * RolloutInputs::COUNT * threads doubles (input staging).
+// Dynamic shared memory: rollout_smem_bytes<M, kInit>(PB) (input staging, shared by a problem's candidates).
 // ---------------------------------------------------------------------------------
 // number of doubles one rollout stage reads per thread
 template <typename M, bool kInit>
@@ -215,23 +215,64 @@ struct RolloutInputs {
                          O_SC = O_X + (kInit ? 0 : X), COUNT = O_SC + NSC;
 };
 
-// `stage_in`: this block's staging area in shared memory, [2][COUNT][nt] doubles
+// where stage t of one staged item lives: base + t * stride (+ problem or scene index)
+struct StageSource {
+    const double* base;
+    size_t stride;
+};
+
+constexpr int kRolloutSlots = 3;                             // stages in flight in the staging ring
+
+template <typename M, bool kInit>
+__host__ __device__ inline size_t rollout_smem_bytes(int problems_per_block) {
+    using RI = RolloutInputs<M, kInit>;
+    return sizeof(StageSource) * RI::COUNT + sizeof(double) * kRolloutSlots * RI::COUNT * problems_per_block;
+}
+
+template <typename M, bool kInit>
+__device__ __forceinline__ StageSource rollout_source(const tplb_batch& q, const Workspace& ws, int e) {
+    using RI = RolloutInputs<M, kInit>;
+    constexpr int X = M::X, U = M::U, NSC = M::NUM_STAGE_CONSTS;
+    const size_t B = q.batch;
+    if (e < RI::O_K) return {q.u + (e - RI::O_U) * B, U * B};
+    if (e < RI::O_HI) return {q.k + (e - RI::O_K) * B, U * B};
+    if (e < RI::O_LO) return {q.u_max + (e - RI::O_HI) * B, U * B};
+    if (e < RI::O_KK) return {q.u_min + (e - RI::O_LO) * B, U * B};
+    if (e < RI::O_X) return {q.K + (e - RI::O_KK) * B, (size_t)U * X * B};
+    if (e < RI::O_SC) return {q.x + (e - RI::O_X) * B, X * B};
+    return {ws.stage_consts + (size_t)(e - RI::O_SC) * q.scenes, (size_t)NSC * q.scenes};
+}
+
+// One thread = one (problem, step size).  All step sizes of a problem read the same inputs
+// (u, k, bounds, K, x, stage constants of stage t), so the block stages them ONCE per problem:
+// `smem` = StageSource[COUNT] followed by a ring of kRolloutSlots stages, [slot][COUNT][PB]
+// doubles.  The candidates of a problem share the copies of a stage (item e is copied by
+// candidate e mod blockDim.y), asynchronously and one stage ahead; one __syncthreads per
+// stage publishes them.  With three slots the copy of stage t+2 can never overwrite what a
+// slower warp still reads for stage t.  `live` == false: the thread only keeps the barriers.
 template <typename M, typename R, bool kInit, int kScheme>
-__device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace& ws, int b, int ai,
-                                            double* stage_in, int tid, int nt) {
+__device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace& ws, int b, int ai, bool live,
+                                            unsigned char* smem) {
     using D = Dims<M>;
     using RI = RolloutInputs<M, kInit>;
     constexpr int X = D::X, U = D::U, NSC = D::NSC;
     const int B = q.batch;
+    const int px = threadIdx.x, pbn = blockDim.x, yy = threadIdx.y, na = blockDim.y;
+    StageSource* src = reinterpret_cast<StageSource*>(smem);
+    double* stage_in = reinterpret_cast<double*>(smem + sizeof(StageSource) * RI::COUNT);
+    for (int e = yy * pbn + px; e < RI::COUNT; e += pbn * na) src[e] = rollout_source<M, kInit>(q, ws, e);
+
     if (kInit) {
-        ws.counters[b] = 0;
-        ws.counters[(size_t)B + b] = 0;
-        ws.counters[(size_t)2 * B + b] = 1;                      // the initial rollout itself
-    } else if (!ws.running[b]) {
-        return;
+        if (live) {
+            ws.counters[b] = 0;
+            ws.counters[(size_t)B + b] = 0;
+            ws.counters[(size_t)2 * B + b] = 1;                  // the initial rollout itself
+        }
+    } else {
+        live = live && ws.running[b];
     }
     const int T = q.horizon;
-    const int scene = __ldg(q.scene_index + b);
+    const int scene = live ? __ldg(q.scene_index + b) : 0;
     const ParamView<R> P = param_view_scene<R>(q, scene);
     const bool second_order = q.use_quadratic_terms != 0;
 
@@ -243,96 +284,80 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
     double* cu = kInit ? nullptr : ws.cand_u + (size_t)ai * q.t_max * U * B + b;
     const int iB = B;                                        // component stride inside a stage
 
-    // Everything stage t reads from global memory is copied asynchronously into this thread's
-    // column of the staging area one stage ahead (double buffered); the dynamics chain of stage
-    // t hides the latency of stage t+1.
-    auto slot = [&](int buf, int item) { return stage_in + ((size_t)buf * RI::COUNT + item) * nt + tid; };
+    auto slot = [&](int buf, int item) { return stage_in + ((size_t)buf * RI::COUNT + item) * pbn + px; };
     auto fetch = [&](int t, int buf) {
-        const size_t su = (size_t)t * U * B + b;
-#pragma unroll
-        for (int d = 0; d < U; ++d) {
-            async_copy8(slot(buf, RI::O_U + d), q.u + su + d * iB);
-            if (!kInit) {
-                async_copy8(slot(buf, RI::O_K + d), q.k + su + d * iB);
-                async_copy8(slot(buf, RI::O_HI + d), q.u_max + su + d * iB);
-                async_copy8(slot(buf, RI::O_LO + d), q.u_min + su + d * iB);
-            }
+        for (int e = yy; e < RI::COUNT; e += na) {
+            const StageSource s = src[e];
+            async_copy8(slot(buf, e), s.base + (size_t)t * s.stride + (e < RI::O_SC ? b : scene));
         }
-        if (!kInit) {
-            if (second_order) {
-                const double* Kt = q.K + (size_t)t * U * X * B + b;
-#pragma unroll
-                for (int e = 0; e < U * X; ++e) async_copy8(slot(buf, RI::O_KK + e), Kt + e * iB);
-            }
-            const double* xt = q.x + (size_t)t * X * B + b;
-#pragma unroll
-            for (int j = 0; j < X; ++j) async_copy8(slot(buf, RI::O_X + j), xt + j * iB);
-        }
-        const double* st = ws.stage_consts + (size_t)t * NSC * q.scenes + scene;
-#pragma unroll
-        for (int j = 0; j < NSC; ++j) async_copy8(slot(buf, RI::O_SC + j), st + j * q.scenes);
     };
 
     R xn[X];
-#pragma unroll
-    for (int i = 0; i < X; ++i) {
-        xn[i] = R(q.x[(size_t)i * B + b]);
-        if (!kInit) __stcs(cx + (size_t)i * B, (double)xn[i]);
-    }
-
-    fetch(0, 0);
-    async_commit();
-    for (int t = 0; t < T; ++t) {
-        const int buf = t & 1;
-        if (t + 1 < T) fetch(t + 1, buf ^ 1);
-        async_commit();                                      // (possibly empty) group of stage t+1
-        async_wait_all_but_one();                            // stage t has landed
-
-        R un[U], xnext[X], sc[D::NSCs];
-#pragma unroll
-        for (int d = 0; d < U; ++d) {
-            const R ud = R(*slot(buf, RI::O_U + d));
-            if (kInit) {
-                un[d] = ud;
-            } else if (second_order) {
-                R v = R(*slot(buf, RI::O_K + d)) * alpha + ud;
-#pragma unroll
-                for (int j = 0; j < X; ++j)
-                    v += R(*slot(buf, RI::O_KK + d * X + j)) * (xn[j] - R(*slot(buf, RI::O_X + j)));
-                const R hi = R(*slot(buf, RI::O_HI + d)), lo = R(*slot(buf, RI::O_LO + d));
-                const R capped = (hi < v) ? hi : v;               // optim.c:755-758
-                un[d] = (lo > capped) ? lo : capped;
-            } else {
-                un[d] = ud - R(*slot(buf, RI::O_K + d)) * alpha;          // optim.c:803-804
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < NSC; ++j) sc[j] = R(*slot(buf, RI::O_SC + j));
-        if (!kInit) {
-            double* cut = cu + (size_t)t * U * B;
-#pragma unroll
-            for (int d = 0; d < U; ++d) __stcs(cut + d * iB, (double)un[d]);   // streaming: keep K, k, x, u in L2
-        }
-        step_state<M, kScheme>(P, xn, un, sc, R(t), R(q.dt), xnext);
-        double* cxt = cx + (size_t)(t + 1) * X * B;
+    if (live) {
 #pragma unroll
         for (int i = 0; i < X; ++i) {
-            xn[i] = xnext[i];
-            if (kInit) cxt[i * iB] = xnext[i];
-            else __stcs(cxt + i * iB, (double)xnext[i]);
+            xn[i] = R(q.x[(size_t)i * B + b]);
+            if (!kInit) __stcs(cx + (size_t)i * B, (double)xn[i]);
         }
+    }
+
+    __syncthreads();                                         // source table written
+    if (live) fetch(0, 0);
+    async_commit();
+    int buf = 0;
+    for (int t = 0; t < T; ++t) {
+        const int nxt = buf + 1 == kRolloutSlots ? 0 : buf + 1;
+        if (live && t + 1 < T) fetch(t + 1, nxt);
+        async_commit();                                      // (possibly empty) group of stage t+1
+        async_wait_all_but_one();                            // this thread's share of stage t has landed
+        __syncthreads();                                     // ... and everybody else's
+
+        if (live) {
+            R un[U], xnext[X], sc[D::NSCs];
+#pragma unroll
+            for (int d = 0; d < U; ++d) {
+                const R ud = R(*slot(buf, RI::O_U + d));
+                if (kInit) {
+                    un[d] = ud;
+                } else if (second_order) {
+                    R v = R(*slot(buf, RI::O_K + d)) * alpha + ud;
+#pragma unroll
+                    for (int j = 0; j < X; ++j)
+                        v += R(*slot(buf, RI::O_KK + d * X + j)) * (xn[j] - R(*slot(buf, RI::O_X + j)));
+                    const R hi = R(*slot(buf, RI::O_HI + d)), lo = R(*slot(buf, RI::O_LO + d));
+                    const R capped = (hi < v) ? hi : v;               // optim.c:755-758
+                    un[d] = (lo > capped) ? lo : capped;
+                } else {
+                    un[d] = ud - R(*slot(buf, RI::O_K + d)) * alpha;          // optim.c:803-804
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NSC; ++j) sc[j] = R(*slot(buf, RI::O_SC + j));
+            if (!kInit) {
+                double* cut = cu + (size_t)t * U * B;
+#pragma unroll
+                for (int d = 0; d < U; ++d) __stcs(cut + d * iB, (double)un[d]);   // streaming: keep K, k, x, u in L2
+            }
+            step_state<M, kScheme>(P, xn, un, sc, R(t), R(q.dt), xnext);
+            double* cxt = cx + (size_t)(t + 1) * X * B;
+#pragma unroll
+            for (int i = 0; i < X; ++i) {
+                xn[i] = xnext[i];
+                if (kInit) cxt[i * iB] = xnext[i];
+                else __stcs(cxt + i * iB, (double)xnext[i]);
+            }
+        }
+        buf = nxt;
     }
 }
 
 template <typename M, typename R, int PB, bool kInit, int kScheme, int kMinBlocks>
 __global__ void __launch_bounds__(PB * (kInit ? 1 : kAlphas), kMinBlocks)
 rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int a_begin, const int32_t* list) {
-    extern __shared__ double stage_in[];                   // [2][RolloutInputs::COUNT][threads]
+    extern __shared__ __align__(16) unsigned char rollout_smem[];
     const int ai = kInit ? 0 : a_begin + threadIdx.y;      // blockDim.y = candidates of this launch
     const int b = problem_of(list, ws.pending_count, blockIdx.x * PB + threadIdx.x, q.batch);
-    if (b < 0) return;
-    dev_rollout<M, R, kInit, kScheme>(q, ws, b, ai, stage_in, threadIdx.y * PB + threadIdx.x,
-                                   blockDim.x * blockDim.y);
+    dev_rollout<M, R, kInit, kScheme>(q, ws, b < 0 ? 0 : b, ai, b >= 0, rollout_smem);
 }
 
 // ---------------------------------------------------------------------------------
