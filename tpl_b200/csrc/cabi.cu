@@ -261,8 +261,7 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
             else launch_rollout<R, false>(q, ws, st, 0, tplb::kAlphas, nullptr);
             prof.after(TPLB_K_ROLLOUT);
             prof.before();
-            tplb::stage_cost_kernel<Model, R><<<dim3(sgx, T + 1, R1), sb, 0, st>>>(
-                q, ws, ws.cand_x, ws.cand_u, cx_stride, cu_stride, 1, 0, nullptr);
+            tplb::stage_cost_round1_kernel<Model, R><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
             prof.after(TPLB_K_STAGE_COST);
             prof.before();
             tplb::select_kernel<PB, 1><<<(B + PB - 1) / PB, dim3(PB, R1), 0, st>>>(q, ws);
@@ -275,7 +274,7 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
                 prof.after(TPLB_K_ROLLOUT);
             }
             prof.before();
-            tplb::stage_cost_kernel<Model, R><<<dim3(sgx, T + 1, R2), sb, 0, st>>>(
+            tplb::stage_cost_kernel<Model, R><<<dim3(sgx < 8 ? sgx : 8, T + 1, R2), sb, 0, st>>>(
                 q, ws, ws.cand_x, ws.cand_u, cx_stride, cu_stride, 1, R1, ws.pending);
             prof.after(TPLB_K_STAGE_COST);
             prof.before();

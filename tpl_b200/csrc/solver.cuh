@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(PB * (kInit ? 1 : kAlphas), kMinBlocks)
 rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int a_begin, const int32_t* list) {
     extern __shared__ __align__(16) unsigned char rollout_smem[];
     const int ai = kInit ? 0 : a_begin + threadIdx.y;      // blockDim.y = candidates of this launch
+    if (list && blockIdx.x * PB >= *ws.pending_count) return;   // block-uniform: nothing pending here
     const int b = problem_of(list, ws.pending_count, blockIdx.x * PB + threadIdx.x, q.batch);
     dev_rollout<M, R, kInit, kScheme>(q, ws, b < 0 ? 0 : b, ai, b >= 0, rollout_smem);
 }
@@ -400,13 +401,57 @@ __device__ __forceinline__ void dev_stage_cost(const tplb_batch& q, const Worksp
     ws.cost_terms[((size_t)a * (q.t_max + 1) + t) * B + b] = c;
 }
 
+// One thread = one (problem, stage, candidate).  With a pending list the x-blocks stride over
+// the list, so the grid can stay small when few problems are pending.
 template <typename M, typename R>
 __global__ void stage_cost_kernel(const __grid_constant__ tplb_batch q, Workspace ws,
                                   const double* xs, const double* us, size_t x_stride, size_t u_stride,
                                   int check_running, int a_begin, const int32_t* list) {
-    const int b = problem_of(list, ws.pending_count, blockIdx.x * blockDim.x + threadIdx.x, q.batch);
-    if (b < 0) return;
-    dev_stage_cost<M, R>(q, ws, xs, us, x_stride, u_stride, check_running, b, blockIdx.y, a_begin + blockIdx.z);
+    const int n = list ? *ws.pending_count : q.batch;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int b = list ? list[i] : i;
+        dev_stage_cost<M, R>(q, ws, xs, us, x_stride, u_stride, check_running, b, blockIdx.y, a_begin + blockIdx.z);
+    }
+}
+
+// Round 1 of the line search: one thread evaluates BOTH first-round candidates of its
+// (problem, stage), so the multipliers, weights and stage constants are read once and the
+// two evaluations interleave.  grid (ceil(B/128), T+1).
+template <typename M, typename R>
+__global__ void stage_cost_round1_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
+    using D = Dims<M>;
+    constexpr int X = D::X, U = D::U, C = D::C;
+    const int B = q.batch, T = q.horizon, t = blockIdx.y;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || !ws.running[b]) return;
+    const size_t x_stride = (size_t)(q.t_max + 1) * X * B, u_stride = (size_t)q.t_max * U * B;
+    const int scene = __ldg(q.scene_index + b);
+    const ParamView<R> P = param_view_scene<R>(q, scene);
+    R sc[D::NSCs], x[kRound1][X], c[kRound1];
+    load_stage_consts<M, R>(q, ws, scene, t, sc);
+#pragma unroll
+    for (int a = 0; a < kRound1; ++a)
+#pragma unroll
+        for (int i = 0; i < X; ++i) x[a][i] = R(ws.cand_x[a * x_stride + ((size_t)t * X + i) * B + b]);
+    if (t < T) {
+        R u[kRound1][U], lam[D::Cs], w[D::Cs];
+#pragma unroll
+        for (int a = 0; a < kRound1; ++a)
+#pragma unroll
+            for (int i = 0; i < U; ++i) u[a][i] = R(ws.cand_u[a * u_stride + ((size_t)t * U + i) * B + b]);
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) {
+            lam[cc] = R(q.lagrange_multiplier[((size_t)t * C + cc) * B + b]);
+            w[cc] = R(q.barrier_weight[(size_t)cc * B + b]);
+        }
+#pragma unroll
+        for (int a = 0; a < kRound1; ++a) M::stage_cost(P, x[a], u[a], lam, w, sc, R(t), R(q.dt), &c[a]);
+    } else {
+#pragma unroll
+        for (int a = 0; a < kRound1; ++a) M::end_cost(P, x[a], sc, R(T), R(q.dt), &c[a]);
+    }
+#pragma unroll
+    for (int a = 0; a < kRound1; ++a) ws.cost_terms[((size_t)a * (q.t_max + 1) + t) * B + b] = c[a];
 }
 
 // trajCosts of the initial rollout: sum in the reference's order (optim.c:1099-1111)
