@@ -377,26 +377,80 @@ def run_ours(a):
         flops_step = sum(flops.values())
         launches = sum(c for _, c in prof.values())
         total_prof_ms = sum(ms for ms, _ in prof.values())
-        dom = max(prof, key=lambda k: prof[k][0])
-        dom_ms, dom_n = prof[dom]
         peak = opt.measure_fp64_tflops()
-        achieved = flops.get(dom, 0) / (dom_ms * 1e-3) / 1e12
         ms_per_step = elapsed_ms / a.steps
         step_tf = flops_step / (ms_per_step * 1e-3) / 1e12
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fd:
                 hbm_peak = json.load(fd)["hbm_gbs"]
+            hbm_src = "MEASURED_PEAKS.json hbm_gbs (copy bandwidth, burst)"
         except (OSError, KeyError, ValueError):
             hbm_peak = 6650.0
-        # DRAM bytes and FP64-pipe activity of the hot kernels from the committed ncu capture
-        # (profiles/ncu_traffic.json); only valid for the default workload
+            hbm_src = "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+        # ---- roofline: HBM -------------------------------------------------------------
+        # With the GPU full (`depth` batches in flight) every hot kernel streams its operands
+        # from HBM: the working set of ONE batch (derivative records, K, k, x, u, candidates)
+        # is already larger than L2.  Kernels of different streams overlap, so they cannot be
+        # timed one by one inside the timed region; their durations are taken from the same
+        # number of problems (depth x B) in one batch, one launch at a time (CUDA events on the
+        # launching stream).  Algorithmic bytes per problem and stage:
+        info = opt._info
+        X_, U_, C_, REC = opt.X, opt.U, opt.C, info["deriv_compact"]
+        R1 = 2                                           # candidates of the first line-search round
+        two_round = a.line_search_rounds == 2 or (a.line_search_rounds == 0 and B * depth >= 16384)
+        step_copy = 4 * (X_ + U_)        # accept: winner -> x,u and x,k -> prev_x,prev_k (read + write)
+        abytes = {                       # doubles moved per (problem, stage, launch)
+            # x, u, multipliers in, derivative record out (+ the accept when it is folded in)
+            "linearize": (X_ + U_) + C_ + REC if two_round else step_copy + C_ + REC,
+            "accept": step_copy,
+            # record + u + bounds in, K and k out
+            "backward": REC + 3 * U_ + U_ * X_ + U_,
+            # u, k, bounds, K, x in; R1 candidates out
+            "rollout": 4 * U_ + U_ * X_ + X_ + R1 * (X_ + U_),
+            # R1 candidates + multipliers in, R1 terms out
+            "stage_cost": R1 * (X_ + U_) + C_ + R1,
+        }
+        sat = None
+        Bs = B * depth
+        if depth > 1 and Bs <= 131072:
+            pbs = sc.mpc_time(batch=Bs, horizon=T, max_iterations=I, forced=True, seed0=rank * B)
+            big = sc.apply_to_batched(BatchedOptim(lib, batch=Bs, horizon_max=T), pbs)
+            big.line_search_rounds = a.line_search_rounds
+            big.update()                                  # warm-up
+            sc.apply_to_batched(big, pbs)                 # fresh problems again
+            big.mu, big.mu_step = 0.0, 0
+            torch.cuda.synchronize()
+            sat = big.update_profiled()
+            torch.cuda.synchronize()
+            del big
+            torch.cuda.empty_cache()
+        src_prof, src_B = (sat, Bs) if sat is not None else (prof, B)
+        hot = {k: v for k, v in src_prof.items() if k in abytes}
+        dom = max(hot, key=lambda k: hot[k][0])
+        dom_ms, dom_n = hot[dom]
+        # rollout / stage_cost: round 2 touches only the few pending problems, so the bytes are
+        # those of round 1 while the time is that of both rounds.  linearize: the first launch of
+        # an update has no step to accept.
+        iters = I * pb.max_lg_iterations
+        doubles_update = {k: v * iters for k, v in abytes.items()}
+        if not two_round:                # folded: the first linearize of an update has nothing to accept,
+            doubles_update["linearize"] -= 3 * (X_ + U_) * pb.max_lg_iterations
+            doubles_update["accept"] = step_copy * pb.max_lg_iterations   # ... the last step has its own launch
+        gbs = {k: doubles_update[k] * 8.0 * src_B * T / (ms * 1e-3) / 1e9 for k, (ms, n) in hot.items()}
+        bytes_solve = sum(doubles_update.values()) * 8.0 * T
+        step_gbs = bytes_solve * value / world / 1e9
+        # DRAM bytes of the hot kernels from the committed ncu capture (profiles/ncu_traffic.json),
+        # per problem and stage, scaled to this launch
         ncu = {}
         try:
-            if (B, T) == (4096, 100):
-                with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fd:
-                    ncu = json.load(fd)["kernels"]
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fd:
+                ncu = json.load(fd)["kernels"]
         except (OSError, KeyError, ValueError):
             ncu = {}
+        traffic = None
+        if dom in ncu and (T, MODEL) == (100, "trajectory_tracking_mpc_time"):
+            traffic = ncu[dom]["dram_bytes_per_problem_stage"] * src_B * T
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -416,18 +470,25 @@ def run_ours(a):
             "gpu_launches": launches * a.steps,
             "gpu_launches_per_step": launches,
             "roofline": {
-                "bound": "fp64", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak if peak > 0 else None,
-                "traffic": ncu.get(dom, {}).get("dram_bytes_per_launch"),
-                "fp64_pipe_active_pct_ncu": ncu.get(dom, {}).get("fp64_pipe_active_pct"),
-                "peak_source": "DFMA loop measured live by tplb_measure_fp64_tflops (MEASURED_PEAKS.json has no fp64 entry)",
-                "algorithmic_flops_per_launch": flops.get(dom, 0) / max(dom_n, 1),
-                "avg_launch_ms": dom_ms / max(dom_n, 1),
-                "special_function_calls_excluded": True,
+                "bound": "hbm", "kernel": dom, "achieved": gbs[dom], "peak": hbm_peak, "unit": "GB/s",
+                "frac": gbs[dom] / hbm_peak, "traffic": traffic,
+                "peak_source": hbm_src,
+                "algorithmic_bytes_per_launch": doubles_update[dom] * 8.0 * src_B * T / iters,
+                "avg_launch_ms": dom_ms / iters,
+                "timed_on": f"{src_B} problems in one batch (the {depth} x {B} in flight overlap and cannot be "
+                            "timed per kernel), CUDA events around every launch",
+                "all_kernels_gbs": {k: round(v, 1) for k, v in gbs.items()},
+                "all_kernels_frac": {k: round(v / hbm_peak, 4) for k, v in gbs.items()},
             },
-            "roofline_step": {"achieved": step_tf, "peak": peak, "unit": "TFLOP/s",
+            "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": step_gbs / hbm_peak,
+                              "algorithmic_bytes_per_solve": bytes_solve},
+            "roofline_fp64": {"achieved": step_tf, "peak": peak, "unit": "TFLOP/s",
                               "frac": step_tf / peak if peak > 0 else None,
-                              "algorithmic_flops_per_solve": flops_step / B},
+                              "algorithmic_flops_per_solve": flops_step / B,
+                              "peak_source": "DFMA loop measured live by tplb_measure_fp64_tflops",
+                              "special_function_calls_excluded": True},
+            "kernel_ms_saturated": ({k: round(ms, 4) for k, (ms, _) in sat.items()} if sat else None),
             "kernel_ms": {k: round(ms, 4) for k, (ms, _) in prof.items()},
             "kernel_share": {k: round(ms / total_prof_ms, 4) for k, (ms, _) in prof.items()},
             "work_per_solve": {"linearisations": lin / B, "backward_sweeps": bwd / B, "rollouts": roll / B},

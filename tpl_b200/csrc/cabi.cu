@@ -227,6 +227,11 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
     const size_t cu_stride = (size_t)q.t_max * Model::U * B;
     constexpr int R1 = tplb::kRound1, R2 = tplb::kAlphas - tplb::kRound1;
     const bool split_rollouts = two_round_rollouts(q);
+    // Accepting the step inside the next linearize saves a launch and a pass over x, u while
+    // launches are latency-bound; with the GPU full the separate copy kernel (high occupancy,
+    // at the HBM roofline) plus a plain linearize is faster than the folded one.
+    bool fold_accept = !split_rollouts;
+    if (const char* e = std::getenv("TPLB_FOLD_ACCEPT")) fold_accept = std::atoi(e) != 0;
 
     prof.before();
     tplb::stage_constants_kernel<Model><<<dim3((S + sb - 1) / sb, T + 1), sb, 0, st>>>(q, ws);
@@ -245,7 +250,7 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
         prof.after(TPLB_K_MULTIPLIER);
         for (int s = 0; s < q.max_iterations; ++s) {
             prof.before();
-            if (s == 0) tplb::linearize_kernel<Model, R, false, false><<<dim3(sgx, T), sb, 0, st>>>(q, ws);
+            if (s == 0 || !fold_accept) tplb::linearize_kernel<Model, R, false, false><<<dim3(sgx, T), sb, 0, st>>>(q, ws);
             else tplb::linearize_kernel<Model, R, false, true><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
             prof.after(TPLB_K_LINEARIZE);
             prof.before();
@@ -280,6 +285,11 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
             prof.before();
             tplb::select_kernel<PB, 2><<<(B + PB - 1) / PB, dim3(PB, R2), 0, st>>>(q, ws);
             prof.after(TPLB_K_SELECT);
+            if (!fold_accept && s + 1 < q.max_iterations) {
+                prof.before();
+                tplb::accept_kernel<Model><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
+                prof.after(TPLB_K_ACCEPT);
+            }
         }
         if (q.max_iterations > 0) {
             prof.before();
