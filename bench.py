@@ -411,6 +411,9 @@ def run_ours(a):
             # R1 candidates + multipliers in, R1 terms out
             "stage_cost": R1 * (X_ + U_) + C_ + R1,
         }
+        if two_round:                    # the rollouts add up the stage costs themselves (+ multipliers in)
+            abytes["rollout"] += C_
+            abytes["stage_cost"] = 0
         sat = None
         Bs = B * depth
         if depth > 1 and Bs <= 131072:
@@ -426,7 +429,7 @@ def run_ours(a):
             del big
             torch.cuda.empty_cache()
         src_prof, src_B = (sat, Bs) if sat is not None else (prof, B)
-        hot = {k: v for k, v in src_prof.items() if k in abytes}
+        hot = {k: v for k, v in src_prof.items() if k in abytes and v[0] > 0}
         dom = max(hot, key=lambda k: hot[k][0])
         dom_ms, dom_n = hot[dom]
         # rollout / stage_cost: round 2 touches only the few pending problems, so the bytes are
@@ -438,7 +441,7 @@ def run_ours(a):
             doubles_update["linearize"] -= 3 * (X_ + U_) * pb.max_lg_iterations
             doubles_update["accept"] = step_copy * pb.max_lg_iterations   # ... the last step has its own launch
         gbs = {k: doubles_update[k] * 8.0 * src_B * T / (ms * 1e-3) / 1e9 for k, (ms, n) in hot.items()}
-        bytes_solve = sum(doubles_update.values()) * 8.0 * T
+        bytes_solve = sum(doubles_update[k] for k in hot) * 8.0 * T
         step_gbs = bytes_solve * value / world / 1e9
         # DRAM bytes of the hot kernels from the committed ncu capture (profiles/ncu_traffic.json),
         # per problem and stage, scaled to this launch

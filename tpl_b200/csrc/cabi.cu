@@ -164,15 +164,15 @@ namespace {
 constexpr int PB = 32;                                     // problems per rollout / select block
 // rollouts of candidates [a_begin, a_begin + a_count) for every problem (list == NULL) or
 // for the problems of the pending list
-template <typename R, bool kInit>
+template <typename R, bool kInit, bool kCost = false>
 void launch_rollout(const tplb_batch& q, const tplb::Workspace& ws, cudaStream_t st,
                     int a_begin, int a_count, const int32_t* list) {
     const dim3 grid((q.batch + PB - 1) / PB), block(PB, kInit ? 1 : a_count);
-    const bool dense = !kInit && q.batch >= 16384;         // enough blocks to want 2 per SM
-    const size_t smem = tplb::rollout_smem_bytes<Model, kInit>(PB);
+    const bool dense = !kInit && !kCost && q.batch >= 16384;         // enough blocks to want 2 per SM
+    const size_t smem = tplb::rollout_smem_bytes<Model, kInit, kCost>(PB);
 #define TPLB_ROLLOUT_K(SCHEME, MINB)                                                                  \
     do {                                                                                              \
-        auto kern = tplb::rollout_kernel<Model, R, PB, kInit, SCHEME, MINB>;                             \
+        auto kern = tplb::rollout_kernel<Model, R, PB, kInit, SCHEME, MINB, kCost>;                           \
         static bool configured = false;                                                               \
         if (!configured) {                                                                            \
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);      \
@@ -180,8 +180,9 @@ void launch_rollout(const tplb_batch& q, const tplb::Workspace& ws, cudaStream_t
         }                                                                                             \
         kern<<<grid, block, smem, st>>>(q, ws, a_begin, list);                                        \
     } while (0)
-#define TPLB_ROLLOUT(SCHEME)                              \
-    if (dense) TPLB_ROLLOUT_K(SCHEME, (kInit ? 1 : 2));   \
+#define TPLB_ROLLOUT(SCHEME)                                          \
+    if constexpr (kCost) TPLB_ROLLOUT_K(SCHEME, 1);                   \
+    else if (dense) TPLB_ROLLOUT_K(SCHEME, (kInit ? 1 : 2));          \
     else TPLB_ROLLOUT_K(SCHEME, 1)
     switch (q.integrator_type) {
         case TPLB_EULER: TPLB_ROLLOUT(TPLB_EULER); break;
@@ -232,6 +233,8 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
     // at the HBM roofline) plus a plain linearize is faster than the folded one.
     bool fold_accept = !split_rollouts;
     if (const char* e = std::getenv("TPLB_FOLD_ACCEPT")) fold_accept = std::atoi(e) != 0;
+    bool sum_in_rollout = split_rollouts;
+    if (const char* e = std::getenv("TPLB_SUM_IN_ROLLOUT")) sum_in_rollout = split_rollouts && std::atoi(e) != 0;
 
     prof.before();
     tplb::stage_constants_kernel<Model><<<dim3((S + sb - 1) / sb, T + 1), sb, 0, st>>>(q, ws);
@@ -260,31 +263,47 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
                 tplb::backward_first_order_kernel<Model, R><<<pgrid, pb, 0, st>>>(q, ws, s);
             prof.after(TPLB_K_BACKWARD);
 
-            // round 1: alpha = 1, 0.1
-            prof.before();
-            if (split_rollouts) launch_rollout<R, false>(q, ws, st, 0, R1, nullptr);
-            else launch_rollout<R, false>(q, ws, st, 0, tplb::kAlphas, nullptr);
-            prof.after(TPLB_K_ROLLOUT);
-            prof.before();
-            tplb::stage_cost_round1_kernel<Model, R><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
-            prof.after(TPLB_K_STAGE_COST);
-            prof.before();
-            tplb::select_kernel<PB, 1><<<(B + PB - 1) / PB, dim3(PB, R1), 0, st>>>(q, ws);
-            prof.after(TPLB_K_SELECT);
-
-            // round 2: alpha = 1e-2 .. 1e-7 for the problems still pending
-            if (split_rollouts) {
+            if (sum_in_rollout) {
+                // GPU full: the rollouts add up their own stage costs, nothing is read twice
                 prof.before();
-                launch_rollout<R, false>(q, ws, st, R1, R2, ws.pending);
+                launch_rollout<R, false, true>(q, ws, st, 0, R1, nullptr);
                 prof.after(TPLB_K_ROLLOUT);
+                prof.before();
+                tplb::select_kernel<PB, 1, true><<<(B + PB - 1) / PB, dim3(PB, R1), 0, st>>>(q, ws);
+                prof.after(TPLB_K_SELECT);
+                prof.before();
+                launch_rollout<R, false, true>(q, ws, st, R1, R2, ws.pending);
+                prof.after(TPLB_K_ROLLOUT);
+                prof.before();
+                tplb::select_kernel<PB, 2, true><<<(B + PB - 1) / PB, dim3(PB, R2), 0, st>>>(q, ws);
+                prof.after(TPLB_K_SELECT);
+            } else {
+                // round 1: alpha = 1, 0.1
+                prof.before();
+                if (split_rollouts) launch_rollout<R, false>(q, ws, st, 0, R1, nullptr);
+                else launch_rollout<R, false>(q, ws, st, 0, tplb::kAlphas, nullptr);
+                prof.after(TPLB_K_ROLLOUT);
+                prof.before();
+                tplb::stage_cost_round1_kernel<Model, R><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
+                prof.after(TPLB_K_STAGE_COST);
+                prof.before();
+                tplb::select_kernel<PB, 1><<<(B + PB - 1) / PB, dim3(PB, R1), 0, st>>>(q, ws);
+                prof.after(TPLB_K_SELECT);
+
+                // round 2: alpha = 1e-2 .. 1e-7 for the problems still pending
+                if (split_rollouts) {
+                    prof.before();
+                    launch_rollout<R, false>(q, ws, st, R1, R2, ws.pending);
+                    prof.after(TPLB_K_ROLLOUT);
+                }
+                prof.before();
+                tplb::stage_cost_kernel<Model, R><<<dim3(sgx < 8 ? sgx : 8, T + 1, R2), sb, 0, st>>>(
+                    q, ws, ws.cand_x, ws.cand_u, cx_stride, cu_stride, 1, R1, ws.pending);
+                prof.after(TPLB_K_STAGE_COST);
+                prof.before();
+                tplb::select_kernel<PB, 2><<<(B + PB - 1) / PB, dim3(PB, R2), 0, st>>>(q, ws);
+                prof.after(TPLB_K_SELECT);
             }
-            prof.before();
-            tplb::stage_cost_kernel<Model, R><<<dim3(sgx < 8 ? sgx : 8, T + 1, R2), sb, 0, st>>>(
-                q, ws, ws.cand_x, ws.cand_u, cx_stride, cu_stride, 1, R1, ws.pending);
-            prof.after(TPLB_K_STAGE_COST);
-            prof.before();
-            tplb::select_kernel<PB, 2><<<(B + PB - 1) / PB, dim3(PB, R2), 0, st>>>(q, ws);
-            prof.after(TPLB_K_SELECT);
             if (!fold_accept && s + 1 < q.max_iterations) {
                 prof.before();
                 tplb::accept_kernel<Model><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);

@@ -207,12 +207,13 @@ __device__ __forceinline__ void step_state(const PV& P, const R* x, const R* u, 
 // Dynamic shared memory: rollout_smem_bytes<M, kInit>(PB) (input staging, shared by a problem's candidates).
 // ---------------------------------------------------------------------------------
 // number of doubles one rollout stage reads per thread
-template <typename M, bool kInit>
+template <typename M, bool kInit, bool kCost = false>
 struct RolloutInputs {
     static constexpr int X = M::X, U = M::U, NSC = M::NUM_STAGE_CONSTS;
     static constexpr int O_U = 0, O_K = O_U + U, O_HI = O_K + (kInit ? 0 : U), O_LO = O_HI + (kInit ? 0 : U),
                          O_KK = O_LO + (kInit ? 0 : U), O_X = O_KK + (kInit ? 0 : U * X),
-                         O_SC = O_X + (kInit ? 0 : X), COUNT = O_SC + NSC;
+                         O_SC = O_X + (kInit ? 0 : X), O_LAM = O_SC + NSC,
+                         COUNT = O_LAM + (kCost ? M::C : 0);   // kCost: the multipliers of the stage cost
 };
 
 // where stage t of one staged item lives: base + t * stride (+ problem or scene index)
@@ -223,15 +224,15 @@ struct StageSource {
 
 constexpr int kRolloutSlots = 3;                             // stages in flight in the staging ring
 
-template <typename M, bool kInit>
+template <typename M, bool kInit, bool kCost = false>
 __host__ __device__ inline size_t rollout_smem_bytes(int problems_per_block) {
-    using RI = RolloutInputs<M, kInit>;
+    using RI = RolloutInputs<M, kInit, kCost>;
     return sizeof(StageSource) * RI::COUNT + sizeof(double) * kRolloutSlots * RI::COUNT * problems_per_block;
 }
 
-template <typename M, bool kInit>
+template <typename M, bool kInit, bool kCost>
 __device__ __forceinline__ StageSource rollout_source(const tplb_batch& q, const Workspace& ws, int e) {
-    using RI = RolloutInputs<M, kInit>;
+    using RI = RolloutInputs<M, kInit, kCost>;
     constexpr int X = M::X, U = M::U, NSC = M::NUM_STAGE_CONSTS;
     const size_t B = q.batch;
     if (e < RI::O_K) return {q.u + (e - RI::O_U) * B, U * B};
@@ -240,7 +241,8 @@ __device__ __forceinline__ StageSource rollout_source(const tplb_batch& q, const
     if (e < RI::O_KK) return {q.u_min + (e - RI::O_LO) * B, U * B};
     if (e < RI::O_X) return {q.K + (e - RI::O_KK) * B, (size_t)U * X * B};
     if (e < RI::O_SC) return {q.x + (e - RI::O_X) * B, X * B};
-    return {ws.stage_consts + (size_t)(e - RI::O_SC) * q.scenes, (size_t)NSC * q.scenes};
+    if (e < RI::O_LAM) return {ws.stage_consts + (size_t)(e - RI::O_SC) * q.scenes, (size_t)NSC * q.scenes};
+    return {q.lagrange_multiplier + (e - RI::O_LAM) * B, (size_t)M::C * B};
 }
 
 // One thread = one (problem, step size).  All step sizes of a problem read the same inputs
@@ -250,17 +252,20 @@ __device__ __forceinline__ StageSource rollout_source(const tplb_batch& q, const
 // candidate e mod blockDim.y), asynchronously and one stage ahead; one __syncthreads per
 // stage publishes them.  With three slots the copy of stage t+2 can never overwrite what a
 // slower warp still reads for stage t.  `live` == false: the thread only keeps the barriers.
-template <typename M, typename R, bool kInit, int kScheme>
+// kCost: the thread also evaluates the stage costs of its candidate and adds them up in the
+// reference's order (optim.c:773-790) -> ws.cand_cost; used when the GPU is full, where
+// re-reading the candidates in a separate cost kernel costs more than the longer chain.
+template <typename M, typename R, bool kInit, int kScheme, bool kCost>
 __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace& ws, int b, int ai, bool live,
                                             unsigned char* smem) {
     using D = Dims<M>;
-    using RI = RolloutInputs<M, kInit>;
+    using RI = RolloutInputs<M, kInit, kCost>;
     constexpr int X = D::X, U = D::U, NSC = D::NSC;
     const int B = q.batch;
     const int px = threadIdx.x, pbn = blockDim.x, yy = threadIdx.y, na = blockDim.y;
     StageSource* src = reinterpret_cast<StageSource*>(smem);
     double* stage_in = reinterpret_cast<double*>(smem + sizeof(StageSource) * RI::COUNT);
-    for (int e = yy * pbn + px; e < RI::COUNT; e += pbn * na) src[e] = rollout_source<M, kInit>(q, ws, e);
+    for (int e = yy * pbn + px; e < RI::COUNT; e += pbn * na) src[e] = rollout_source<M, kInit, kCost>(q, ws, e);
 
     if (kInit) {
         if (live) {
@@ -288,7 +293,7 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
     auto fetch = [&](int t, int buf) {
         for (int e = yy; e < RI::COUNT; e += na) {
             const StageSource s = src[e];
-            async_copy8(slot(buf, e), s.base + (size_t)t * s.stride + (e < RI::O_SC ? b : scene));
+            async_copy8(slot(buf, e), s.base + (size_t)t * s.stride + ((e >= RI::O_SC && e < RI::O_LAM) ? scene : b));
         }
     };
 
@@ -299,6 +304,12 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
             xn[i] = R(q.x[(size_t)i * B + b]);
             if (!kInit) __stcs(cx + (size_t)i * B, (double)xn[i]);
         }
+    }
+    double total = 0.0;
+    R weight[D::Cs];
+    if (kCost && live) {
+#pragma unroll
+        for (int cc = 0; cc < D::C; ++cc) weight[cc] = R(q.barrier_weight[(size_t)cc * B + b]);
     }
 
     __syncthreads();                                         // source table written
@@ -338,6 +349,13 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
 #pragma unroll
                 for (int d = 0; d < U; ++d) __stcs(cut + d * iB, (double)un[d]);   // streaming: keep K, k, x, u in L2
             }
+            if (kCost) {
+                R lam[D::Cs], c;
+#pragma unroll
+                for (int cc = 0; cc < D::C; ++cc) lam[cc] = R(*slot(buf, RI::O_LAM + cc));
+                M::stage_cost(P, xn, un, lam, weight, sc, R(t), R(q.dt), &c);
+                total += (double)c;
+            }
             step_state<M, kScheme>(P, xn, un, sc, R(t), R(q.dt), xnext);
             double* cxt = cx + (size_t)(t + 1) * X * B;
 #pragma unroll
@@ -349,16 +367,23 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
         }
         buf = nxt;
     }
+    if (kCost && live) {
+        R sc[D::NSCs], c;
+        load_stage_consts<M, R>(q, ws, scene, T, sc);
+        M::end_cost(P, xn, sc, R(T), R(q.dt), &c);
+        total += (double)c;
+        ws.cand_cost[(size_t)ai * B + b] = total;
+    }
 }
 
-template <typename M, typename R, int PB, bool kInit, int kScheme, int kMinBlocks>
+template <typename M, typename R, int PB, bool kInit, int kScheme, int kMinBlocks, bool kCost = false>
 __global__ void __launch_bounds__(PB * (kInit ? 1 : kAlphas), kMinBlocks)
 rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int a_begin, const int32_t* list) {
     extern __shared__ __align__(16) unsigned char rollout_smem[];
     const int ai = kInit ? 0 : a_begin + threadIdx.y;      // blockDim.y = candidates of this launch
     if (list && blockIdx.x * PB >= *ws.pending_count) return;   // block-uniform: nothing pending here
     const int b = problem_of(list, ws.pending_count, blockIdx.x * PB + threadIdx.x, q.batch);
-    dev_rollout<M, R, kInit, kScheme>(q, ws, b < 0 ? 0 : b, ai, b >= 0, rollout_smem);
+    dev_rollout<M, R, kInit, kScheme, kCost>(q, ws, b < 0 ? 0 : b, ai, b >= 0, rollout_smem);
 }
 
 // ---------------------------------------------------------------------------------
@@ -1020,7 +1045,8 @@ __device__ __forceinline__ int first_improving(const double (*s_total)[PB], int 
 
 // kRound == 1: block = PB problems x kRound1 candidates, every problem of the batch.
 // kRound == 2: block = PB pending problems x (8 - kRound1) candidates.
-template <int PB, int kRound>
+// kSummed: the rollouts already left the candidate totals in ws.cand_cost.
+template <int PB, int kRound, bool kSummed = false>
 __global__ void __launch_bounds__(PB * (kRound == 1 ? kRound1 : kAlphas - kRound1))
 select_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
     constexpr int NA = kRound == 1 ? kRound1 : kAlphas - kRound1;
@@ -1030,7 +1056,7 @@ select_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
     const int B = q.batch;
     const int b = problem_of(kRound == 1 ? nullptr : ws.pending, ws.pending_count, blockIdx.x * PB + lane, B);
     const bool live = b >= 0 && ws.running[b];
-    s_total[threadIdx.y][lane] = live ? dev_candidate_total(q, ws, b, a) : 0.0;
+    s_total[threadIdx.y][lane] = !live ? 0.0 : kSummed ? ws.cand_cost[(size_t)a * B + b] : dev_candidate_total(q, ws, b, a);
     __syncthreads();
     if (threadIdx.y != 0 || b < 0) return;
     if (!live) {                                             // stopped earlier: nothing to accept
