@@ -292,11 +292,14 @@ def run_ours(a):
     resident_cost_check = float(opt.traj_costs.sum())
 
     # ---- end to end through the public API with host buffers --------------------------
+    names = opt.params.scalar_names
     host = {
         "x0": torch.from_numpy(pb.x0).pin_memory(),
         "u0": torch.from_numpy(pb.u0).pin_memory(),
         "arrays": {k: torch.from_numpy(v).pin_memory() for k, v in pb.arrays.items()},
-        "scalars": {k: torch.from_numpy(v).pin_memory() for k, v in pb.scalars.items()},
+        # all scalar parameters as one (num_scalars, S) block in the solver's order
+        "scalars": torch.from_numpy(np.stack([np.broadcast_to(np.asarray(pb.scalars[k], dtype=np.float64),
+                                                              (opt.scenes,)) for k in names])).pin_memory(),
     }
     # same pipeline; every step uploads all of its inputs and downloads all of its results
     # inside the timed region
@@ -306,19 +309,18 @@ def run_ours(a):
         "c": torch.empty((B,), dtype=torch.float64).pin_memory(),
         "i": torch.empty((2, B), dtype=torch.int32).pin_memory(),
     } for _ in range(depth)]
-    h2d = (host["x0"].numel() + host["u0"].numel()) * 8 + sum(v.numel() * 8 for v in host["arrays"].values()) \
-        + sum(v.numel() * 8 for v in host["scalars"].values())
+    h2d = (host["x0"].numel() + host["u0"].numel() + host["scalars"].numel()) * 8 \
+        + sum(v.numel() * 8 for v in host["arrays"].values())
     d2h = (outs[0]["x"].numel() + outs[0]["u"].numel() + outs[0]["c"].numel()) * 8 + outs[0]["i"].numel() * 4
 
     def step_e2e():
         with pipe.next() as slot:
             o, out = slot.opt, outs[slot.index]
-            for k, v in host["scalars"].items():
-                setattr(o.params, k, v.to(dev, non_blocking=True))
+            o.params.set_scalars(host["scalars"])
             for k, v in host["arrays"].items():
-                setattr(o.params, k, v.to(dev, non_blocking=True))
-            o.set_initial_state(host["x0"].to(dev, non_blocking=True))
-            o.u = host["u0"].to(dev, non_blocking=True)
+                setattr(o.params, k, v)
+            o.set_initial_state(host["x0"])
+            o.u = host["u0"]
             o.lagrange_multiplier = 0.0
             o.mu = 0.0
             o.mu_step = 0

@@ -578,3 +578,33 @@ def test_batches_in_flight_are_independent(solver_libs):
     for got, want in zip(outs, alone):
         for a, b in zip(got, want):
             assert torch.equal(a, b)
+
+
+def test_uploads_from_pinned_host_buffers(solver_libs):
+    """Setters take host tensors directly (one copy into the solver's buffer, asynchronous for
+    pinned memory); `params.set_scalars` moves all scalars at once.  Same solve as the
+    generic path of `scenarios.apply_to_batched`."""
+    from tpl_b200 import scenarios as sc
+    pb = sc.mpc_time(batch=64, horizon=40, max_iterations=6, forced=True, seed0=4242)
+    ref = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
+    ref.update()
+
+    q = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)        # settings, bounds, shapes
+    names = q.params.scalar_names
+    assert set(names) == set(pb.scalars)
+    q.params.set_scalars(torch.zeros(len(names), q.scenes))
+    for k in pb.arrays:
+        setattr(q.params, k, torch.zeros_like(getattr(q.params, k)))
+    q.set_initial_state(torch.zeros(pb.batch, q.X, dtype=torch.float64))
+    q.u = 0.0
+    packed = torch.from_numpy(np.stack([np.broadcast_to(pb.scalars[k], (q.scenes,)) for k in names])).pin_memory()
+    q.params.set_scalars(packed)
+    for k, v in pb.arrays.items():
+        setattr(q.params, k, torch.from_numpy(v).pin_memory())
+    q.set_initial_state(torch.from_numpy(pb.x0).pin_memory())
+    q.u = torch.from_numpy(pb.u0).pin_memory()
+    q.update()
+    torch.cuda.synchronize()
+    assert torch.equal(q.x, ref.x) and torch.equal(q.u, ref.u) and torch.equal(q.traj_costs, ref.traj_costs)
+    with pytest.raises(ValueError):
+        q.params.set_scalars(torch.zeros(len(names) + 1, q.scenes))

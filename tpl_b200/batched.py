@@ -36,9 +36,18 @@ EULER, HEUN, RK4 = 0, 1, 2
 
 def _as_tensor(value, device, dtype=torch.float64):
     if isinstance(value, torch.Tensor):
-        return value.to(device=device, dtype=dtype)
+        return value.to(device=device, dtype=dtype, non_blocking=True)
     return torch.as_tensor(np.asarray(value, dtype=np.float64 if dtype == torch.float64 else None),
                            dtype=dtype).to(device)
+
+
+def _source(value, dtype=torch.float64):
+    """``value`` as a tensor of ``dtype`` on whatever device it lives on; the copy into the
+    solver's buffer (``dst.copy_(src, non_blocking=True)``) then moves it in one step —
+    asynchronously when ``value`` is a pinned host tensor."""
+    if isinstance(value, torch.Tensor):
+        return value if value.dtype == dtype else value.to(dtype)
+    return torch.as_tensor(np.asarray(value, dtype=np.float64 if dtype == torch.float64 else None), dtype=dtype)
 
 
 def _fit(value, view):
@@ -62,6 +71,29 @@ class BatchedParams:
     def slots(self):
         return list(self._o._info["param_order"])
 
+    @property
+    def scalar_names(self):
+        o = self._o
+        return sorted(o._scalar_index, key=o._scalar_index.get)
+
+    @property
+    def array_names(self):
+        o = self._o
+        return sorted(o._array_index, key=o._array_index.get)
+
+    def set_scalars(self, values):
+        """All scalar parameters in one copy: ``values`` is (len(scalar_names), S) or
+        (len(scalar_names),), rows in ``scalar_names`` order (batched extension: one
+        host->device transfer instead of one per name)."""
+        o = self._o
+        t = _source(values)
+        if t.ndim == 1:
+            t = t.unsqueeze(1)
+        if t.ndim != 2 or t.shape[0] != o._scalars.shape[0] or t.shape[1] not in (1, o.scenes):
+            raise ValueError(f"Expected scalars with shape ({o._scalars.shape[0]}, {o.scenes}), "
+                             f"but found {tuple(t.shape)}")
+        o._scalars.copy_(t.expand_as(o._scalars), non_blocking=True)
+
     def __dir__(self):
         return self.slots + ["slots"]
 
@@ -78,17 +110,21 @@ class BatchedParams:
     def __setattr__(self, n, v):
         o = self._o
         if n in o._scalar_index:
-            o._scalars[o._scalar_index[n]].copy_(_as_tensor(v, o.device).expand(o.scenes))
+            o._scalars[o._scalar_index[n]].copy_(_source(v).expand(o.scenes), non_blocking=True)
         elif n in o._array_index:
-            t = _as_tensor(v, o.device)
+            t = _source(v)
             if t.ndim == 0:
                 raise ValueError(f"parameter {n} is an array")
             if t.ndim == 1:
                 t = t.unsqueeze(0).expand(o.scenes, -1)
             if t.ndim != 2 or t.shape[0] != o.scenes:
                 raise ValueError(f'Expected "{n}" with shape ({o.scenes}, L) or (L,), but found {tuple(t.shape)}')
-            o._arrays[o._array_index[n]] = t.contiguous().clone()
-            o._dirty = True
+            i = o._array_index[n]
+            if o._arrays[i].shape == t.shape:          # same length: refill the buffer in place
+                o._arrays[i].copy_(t, non_blocking=True)
+            else:
+                o._arrays[i] = t.to(o.device).contiguous().clone()
+                o._dirty = True
         else:
             raise AttributeError(f"no parameter named {n!r}")
 
@@ -321,7 +357,7 @@ class BatchedOptim:
             if isinstance(v, (int, float)):
                 view.fill_(float(v))
             else:
-                view.copy_(_fit(_as_tensor(v, self.device), view))
+                view.copy_(_fit(_source(v), view), non_blocking=True)
         elif n in self._STATUS:
             t = self._status[n]
             t.copy_(_as_tensor(v, self.device, t.dtype).expand_as(t))
@@ -338,7 +374,7 @@ class BatchedOptim:
 
     def set_initial_state(self, x0):
         """``opt.x[:, 0] = x0`` for host or device ``x0`` of shape (B, X)."""
-        self._x[0].copy_(_as_tensor(x0, self.device).expand(self.batch, self.X).t())
+        self._x[0].copy_(_source(x0).expand(self.batch, self.X).t(), non_blocking=True)
 
     # -- C ABI plumbing ---------------------------------------------------------------
     def _ensure_workspace(self):
