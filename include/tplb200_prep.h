@@ -1,0 +1,58 @@
+/* tplb200_prep.h — C ABI of the batched profile shaping that runs right before the lateral and
+ * velocity solves of tpl's path/velocity decomposition planner.
+ *
+ * Replaces, for B independent problems at once:
+ *   tplb_rampify_velocity : rampify_profile(v0, a0, lim_v, a_min, a_max, j_min, j_max, v_min, step)
+ *                           library/tpl/planning/utils.py:5-65 (called from
+ *                           planning/path_vel_decomp/velocity_optim.py:219-224)
+ *   tplb_rampify_lateral  : rampify_profile(step, horizon, evasion_sharpness, proj_distance, path,
+ *                           gap, lower, upper)
+ *                           library/tpl/planning/path_vel_decomp/path_optim.py:11-55 (called twice
+ *                           per cycle, path_optim.py:262-278)
+ *
+ * The reference runs them under numba (fastmath) on one problem; both are sequential scans over
+ * the N samples of a profile, so here one thread owns one problem and the batch is the parallel
+ * dimension.  All arrays are DEVICE pointers, fp64, structure of arrays with the problem index
+ * fastest: sample i of problem b is at [i*B + b].  Calls are asynchronous on `stream`
+ * (a cudaStream_t).  Return value 0 or a negative TPLB_PREP_E_* code; tplb_prep_last_error() has the text.
+ * One shared library: libtplb200_prep.so (independent of the per-model solver libraries). */
+#ifndef TPLB200_PREP_H
+#define TPLB200_PREP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TPLB_PREP_API __attribute__((visibility("default")))
+#else
+#define TPLB_PREP_API
+#endif
+
+#define TPLB_PREP_ABI_VERSION 1
+enum { TPLB_PREP_E_ARG = -1 };
+
+TPLB_PREP_API int32_t tplb_prep_abi_version(void);
+TPLB_PREP_API const char* tplb_prep_last_error(void);
+
+/* planning/utils.py:5-65.  lim_v [N][B]; v0, a0 [B] or NULL (= the reference's `None` for every
+ * problem: start from the backward pass' value); profile [N][2][B] (velocity, acceleration). */
+TPLB_PREP_API int32_t tplb_rampify_velocity(int32_t batch, int32_t n, const double* v0, const double* a0,
+                                            const double* lim_v, double a_min, double a_max, double j_min,
+                                            double j_max, double v_min, double step, double* profile,
+                                            void* stream);
+
+/* path_optim.py:11-55.  path_v = column 5 of the reference's `path` array, lower, upper [N][B];
+ * proj_distance [B]; horizon <= N samples are shaped, the remaining samples of the output keep the
+ * reference's initial value -10; d_offset [N][B]. */
+TPLB_PREP_API int32_t tplb_rampify_lateral(int32_t batch, int32_t n, int32_t horizon, double step,
+                                           double evasion_sharpness, const double* proj_distance,
+                                           const double* path_v, double gap, const double* lower,
+                                           const double* upper, double* d_offset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,59 @@
+"""TEST INFRASTRUCTURE — ctypes front end of oracle/prep_oracle.c (one problem per call,
+numpy in / numpy out, the reference functions' argument order).  Not imported by tpl_b200."""
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_D = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+
+def _lib():
+    path = os.path.join(HERE, "lib", "liboracle_prep.so")
+    if not os.path.exists(path):
+        subprocess.run(["make", "-s", "-C", HERE, "lib/liboracle_prep.so"], check=True)
+    lib = C.CDLL(path)
+    lib.tplo_rampify_velocity.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, _D] + \
+        [C.c_double] * 6 + [_D, _D]
+    lib.tplo_rampify_velocity.restype = None
+    lib.tplo_rampify_lateral.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _D, C.c_double,
+                                         _D, _D, _D, _D, _D]
+    lib.tplo_rampify_lateral.restype = None
+    return lib
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = _lib()
+    return _LIB
+
+
+def rampify_velocity(v0, a0, lim_v, a_min, a_max, j_min, j_max, v_min, step):
+    """planning/utils.py:5-65 -> (n, 2)."""
+    lim_v = np.ascontiguousarray(lim_v, dtype=np.float64)
+    n = len(lim_v)
+    scratch, out = np.empty(n), np.empty((n, 2))
+    lib().tplo_rampify_velocity(n, v0 is not None, 0.0 if v0 is None else float(v0),
+                                a0 is not None, 0.0 if a0 is None else float(a0), lim_v,
+                                a_min, a_max, j_min, j_max, v_min, step, scratch, out)
+    return out
+
+
+def rampify_lateral(step, horizon, evasion_sharpness, proj_distance, path, gap, lower, upper):
+    """planning/path_vel_decomp/path_optim.py:11-55 -> (len(path),)."""
+    path = np.asarray(path, dtype=np.float64)
+    path_v = np.ascontiguousarray(path[:, 5])
+    n = len(path_v)
+    lower = np.ascontiguousarray(lower, dtype=np.float64)
+    upper = np.ascontiguousarray(upper, dtype=np.float64)
+    fwd, bwd, out = np.empty(n), np.empty(n), np.empty(n)
+    lib().tplo_rampify_lateral(n, int(horizon), step, evasion_sharpness, float(proj_distance), path_v, gap,
+                               lower, upper, fwd, bwd, out)
+    return out

@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Record golden vectors of the reference's two `rampify_profile` functions (SURVEY.md
+section 8, row f2) by running the REAL reference code under numba:
+
+    library/tpl/planning/utils.py:5-65                        (velocity profile)
+    library/tpl/planning/path_vel_decomp/path_optim.py:11-55  (lateral corridor)
+
+Neither module can be imported here (`tpl.planning/__init__` needs tplcpp, path_optim needs
+objtoolbox), so the function definitions are taken from the reference files by name with `ast`
+at run time and compiled as they stand (same decorator arguments except `cache`, which needs a
+file-backed module).  Nothing of the reference is copied into the repository; only inputs and
+outputs are stored: tests/golden/prep_velocity.npz, tests/golden/prep_lateral.npz.
+
+    python tests/golden/make_golden_prep.py        # needs /root/reference and numba
+"""
+import ast
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+os.environ.setdefault("NUMBA_CACHE_DIR", os.path.join(ROOT, "oracle", "_ref", "numba_cache"))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from tpl_b200 import prep_scenarios as ps  # noqa: E402
+
+REF = "/root/reference/library/tpl"
+
+
+def reference_function(path, name):
+    """Compile function `name` of the reference file `path` in a fresh namespace."""
+    import numba
+    src = open(path).read()
+    tree = ast.parse(src)
+    node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
+    seg = ast.get_source_segment(src, node)
+    deco = "\n".join("@" + ast.get_source_segment(src, d).replace("cache=True, ", "").replace("cache=True", "")
+                     for d in node.decorator_list)
+    ns = {"numba": numba, "np": np}
+    exec(compile(deco + "\n" + seg, path, "exec"), ns)
+    return ns[name]
+
+
+def main():
+    vel = reference_function(os.path.join(REF, "planning", "utils.py"), "rampify_profile")
+    lat = reference_function(os.path.join(REF, "planning", "path_vel_decomp", "path_optim.py"), "rampify_profile")
+
+    cases = ps.velocity_cases()
+    out = {}
+    for i, c in enumerate(cases):
+        res = vel(c["v0"], c["a0"], c["lim_v"].copy(), c["a_min"], c["a_max"], c["j_min"], c["j_max"],
+                  c["v_min"], c["step"])
+        out[f"profile_{i}"] = np.asarray(res)
+    np.savez_compressed(os.path.join(HERE, "prep_velocity.npz"), **out)
+    print("velocity:", len(cases), "cases")
+
+    cases = ps.lateral_cases()
+    out = {}
+    for i, c in enumerate(cases):
+        res = lat(c["step"], c["horizon"], c["evasion_sharpness"], c["proj_distance"], c["path"], c["gap"],
+                  c["lower"], c["upper"])
+        out[f"d_offset_{i}"] = np.asarray(res)
+    np.savez_compressed(os.path.join(HERE, "prep_lateral.npz"), **out)
+    print("lateral:", len(cases), "cases")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,134 @@
+"""Profile shaping in front of the lateral / velocity solves.
+
+CPU: the C restatement (oracle/prep_oracle.c) against golden vectors recorded from the
+reference's own numba functions (tests/golden/make_golden_prep.py); the CUDA library's exports.
+GPU: the batched CUDA kernels (through the C ABI) against those golden vectors and the oracle."""
+
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import prep as oprep
+from tpl_b200 import build, prep, prep_scenarios as ps
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def prep_lib():
+    return build.build_prep()
+
+
+def _vel_oracle(c):
+    return oprep.rampify_velocity(c["v0"], c["a0"], c["lim_v"], c["a_min"], c["a_max"], c["j_min"], c["j_max"],
+                                  c["v_min"], c["step"])
+
+
+def _lat_oracle(c):
+    return oprep.rampify_lateral(c["step"], c["horizon"], c["evasion_sharpness"], c["proj_distance"], c["path"],
+                                 c["gap"], c["lower"], c["upper"])
+
+
+def test_oracle_matches_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "prep_velocity.npz"))
+    for i, c in enumerate(ps.velocity_cases()):
+        np.testing.assert_allclose(_vel_oracle(c), g[f"profile_{i}"], rtol=RTOL, atol=1e-12)
+    g = np.load(os.path.join(GOLDEN, "prep_lateral.npz"))
+    for i, c in enumerate(ps.lateral_cases()):
+        np.testing.assert_allclose(_lat_oracle(c), g[f"d_offset_{i}"], rtol=RTOL, atol=1e-12)
+
+
+def test_library_exports_the_declared_symbols(prep_lib):
+    lib = C.CDLL(prep_lib)
+    for name in prep.EXPORTS:
+        assert hasattr(lib, name), name
+    header = open(os.path.join(os.path.dirname(GOLDEN), "..", "include", "tplb200_prep.h")).read()
+    for name in prep.EXPORTS:
+        assert name + "(" in header
+    lib.tplb_prep_abi_version.restype = C.c_int32
+    assert lib.tplb_prep_abi_version() == prep.ABI_VERSION
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    c = ps.velocity_cases()[0]
+    with pytest.raises(prep.PrepError):
+        prep.rampify_velocity_profile(c["v0"], c["a0"], c["lim_v"][None], c["a_min"], c["a_max"], c["j_min"],
+                                      c["j_max"], c["v_min"], c["step"])
+
+
+@pytest.mark.gpu
+def test_velocity_ramp_matches_golden_and_oracle(prep_lib):
+    g = np.load(os.path.join(GOLDEN, "prep_velocity.npz"))
+    for i, c in enumerate(ps.velocity_cases()):
+        v0 = None if c["v0"] is None else [c["v0"]]
+        a0 = None if c["a0"] is None else [c["a0"]]
+        out = prep.rampify_velocity_profile(v0, a0, c["lim_v"][None], c["a_min"], c["a_max"], c["j_min"],
+                                            c["j_max"], c["v_min"], c["step"])
+        assert out.shape == (1, len(c["lim_v"]), 2)
+        np.testing.assert_allclose(out[0].cpu().numpy(), g[f"profile_{i}"], rtol=RTOL, atol=1e-12)
+    # a ragged-size batch (not a multiple of the block) against the oracle, problem by problem
+    b = ps.velocity_batch(batch=333, n=250, seed0=5000)
+    out = prep.rampify_velocity_profile(b["v0"], b["a0"], b["lim_v"], b["a_min"], b["a_max"], b["j_min"],
+                                        b["j_max"], b["v_min"], b["step"]).cpu().numpy()
+    for k in range(0, 333, 7):
+        want = oprep.rampify_velocity(b["v0"][k], b["a0"][k], b["lim_v"][k], b["a_min"], b["a_max"], b["j_min"],
+                                      b["j_max"], b["v_min"], b["step"])
+        np.testing.assert_allclose(out[k], want, rtol=RTOL, atol=1e-12)
+    # the result never exceeds the (floored) limit and respects the acceleration bounds
+    lim = np.maximum(b["lim_v"], b["v_min"])
+    assert (out[..., 0] <= lim + 1e-12).all()
+    assert (out[:, 1:, 1] <= b["a_max"] + 1e-12).all() and (out[:, 1:, 1] >= b["a_min"] - 1e-12).all()
+
+
+@pytest.mark.gpu
+def test_lateral_ramp_matches_golden_and_oracle(prep_lib):
+    g = np.load(os.path.join(GOLDEN, "prep_lateral.npz"))
+    for i, c in enumerate(ps.lateral_cases()):
+        out = prep.rampify_lateral_profile(c["step"], c["horizon"], c["evasion_sharpness"], [c["proj_distance"]],
+                                           c["path"][None], c["gap"], c["lower"][None], c["upper"][None])
+        assert out.shape == (1, len(c["lower"]))
+        np.testing.assert_allclose(out[0].cpu().numpy(), g[f"d_offset_{i}"], rtol=RTOL, atol=1e-12)
+    b = ps.lateral_batch(batch=205, n=200, seed0=7000)
+    out = prep.rampify_lateral_profile(b["step"], b["horizon"], b["evasion_sharpness"], b["proj_distance"],
+                                       b["path_v"], b["gap"], b["lower"], b["upper"]).cpu().numpy()
+    for k in range(0, 205, 5):
+        path = np.zeros((200, 6))
+        path[:, 5] = b["path_v"][k]
+        want = oprep.rampify_lateral(b["step"], b["horizon"], b["evasion_sharpness"], b["proj_distance"][k], path,
+                                     b["gap"], b["lower"][k], b["upper"][k])
+        np.testing.assert_allclose(out[k], want, rtol=RTOL, atol=1e-12)
+    assert (out >= b["lower"] - 1e-12).all()                  # the shaped bound never cuts into the corridor bound
+    with pytest.raises(prep.PrepError):
+        prep.rampify_lateral_profile(b["step"], 201, b["evasion_sharpness"], b["proj_distance"], b["path_v"],
+                                     b["gap"], b["lower"], b["upper"])
+
+
+@pytest.mark.gpu
+def test_shaped_corridor_feeds_the_lateral_solver(prep_lib, solver_libs):
+    """path_optim.py:262-296: both corridor sides are shaped, the target offset is formed and the
+    three arrays become parameters of the lateral solve — all on the device."""
+    from tpl_b200 import scenarios as sc
+    from tpl_b200.batched import BatchedOptim
+    B, N = 64, 120
+    pb = sc.lateral(batch=B, horizon=N, max_iterations=5, seed0=900)
+    lower_c, upper_c = pb.arrays["d_lower_constr"], pb.arrays["d_upper_constr"]
+    n = lower_c.shape[1]
+    path_v = np.full((B, n), 8.0)
+    proj = np.zeros(B)
+    lo = prep.rampify_lateral_profile(0.5, n, 4.0, proj, path_v, 0.3, lower_c, -upper_c)
+    up = -prep.rampify_lateral_profile(0.5, n, 4.0, -proj, path_v, 0.3, -upper_c, -lower_c)
+    assert bool((lo >= torch.as_tensor(lower_c, device=lo.device) - 1e-12).all())
+    assert bool((up <= torch.as_tensor(upper_c, device=up.device) + 1e-12).all())
+    opt = sc.apply_to_batched(BatchedOptim(solver_libs[pb.model], batch=B, scenes=pb.scenes, horizon_max=N), pb)
+    opt.params.d_lower_constr = lo
+    opt.params.d_upper_constr = up
+    opt.params.d_offset = lo + torch.minimum((up - lo) / 2, torch.full_like(lo, 0.5))
+    opt.update()
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(opt.traj_costs).all())

@@ -126,6 +126,34 @@ def zoo_library_path(name):
     return os.path.join(default_lib_dir(), f"libtplb200_{name}.so")
 
 
+def build_prep(force=False, verbose=False) -> str:
+    """libtplb200_prep.so: the model-independent profile shaping (csrc/prep.cu, include/tplb200_prep.h)."""
+    lib_dir = default_lib_dir()
+    os.makedirs(lib_dir, exist_ok=True)
+    lib_path = os.path.join(lib_dir, "libtplb200_prep.so")
+    h = hashlib.sha1()
+    for fn in (os.path.join(CSRC, "prep.cu"), os.path.join(PKG, "..", "include", "tplb200_prep.h")):
+        with open(fn, "rb") as fd:
+            h.update(fd.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    stamp, stamp_file = h.hexdigest(), lib_path + ".stamp"
+    if not force and os.path.exists(lib_path) and os.path.exists(stamp_file):
+        with open(stamp_file) as fd:
+            if fd.read().strip() == stamp:
+                return lib_path
+    cmd = [nvcc_path(), *NVCC_FLAGS, os.path.join(CSRC, "prep.cu"), "-o", lib_path]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed for prep.cu:\n%s" % res.stdout)
+    if verbose:
+        print(res.stdout)
+    with open(stamp_file, "w") as fd:
+        fd.write(stamp)
+    return lib_path
+
+
 def build_zoo(names=None, force=False, regen=False, verbose=False):
     """Build the shipped problem definitions in-tree; returns {name: path}."""
     from . import optimizers
@@ -146,6 +174,8 @@ def main(argv=None):
     a = ap.parse_args(argv)
     for n, p in build_zoo(a.names or None, force=a.force, regen=a.regen, verbose=a.verbose).items():
         print(f"{n}: {os.path.relpath(p)}")
+    if not a.names:
+        print(f"prep: {os.path.relpath(build_prep(force=a.force, verbose=a.verbose))}")
     return 0
 
 

@@ -1,0 +1,161 @@
+// Batched profile shaping in front of the lateral / velocity solves (include/tplb200_prep.h).
+// One thread = one problem (both routines are scans over the samples with a carried state);
+// arrays are [sample][problem], so every access of a warp is one 256-byte row.
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "../../include/tplb200_prep.h"
+
+namespace {
+
+thread_local char g_error[256] = "";
+
+int fail(int code, const char* msg) {
+    std::snprintf(g_error, sizeof g_error, "%s", msg);
+    return code;
+}
+
+int check_launch(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return 0;
+    std::snprintf(g_error, sizeof g_error, "%s: %s", what, cudaGetErrorString(e));
+    return TPLB_PREP_E_ARG;
+}
+
+// planning/utils.py:5-65.  profile: [N][2][B].
+__global__ void rampify_velocity_kernel(int B, int N, const double* __restrict__ v0, const double* __restrict__ a0,
+                                        const double* __restrict__ lim_v_in, double a_min, double a_max,
+                                        double j_min, double j_max, double v_min, double step,
+                                        double* __restrict__ profile) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    auto lim = [&](int t) { return fmax(lim_v_in[(size_t)t * B + b], v_min); };   // utils.py:17
+    auto pv = [&](int t) -> double& { return profile[((size_t)t * 2 + 0) * B + b]; };
+    auto pa = [&](int t) -> double& { return profile[((size_t)t * 2 + 1) * B + b]; };
+
+    // backward pass, utils.py:24-35
+    double cur_v = lim(N - 1), cur_a = 0.0;
+    pv(0) = 0.0;
+    pa(0) = 0.0;
+    double lim_t = cur_v;                                    // lim_v[t]
+    for (int t = N - 1; t > 0; --t) {
+        pv(t) = cur_v;
+        pa(t) = cur_a;
+        const double lim_prev = lim(t - 1);
+        const double lim_a = fmax(a_min, (cur_v - lim_prev) / step * cur_v);
+        if (lim_a < 0.0) {
+            cur_a = fmax(cur_a + j_min / cur_v * step, lim_a);
+        } else {
+            cur_a = 0.0;
+            cur_v = lim_t;
+        }
+        cur_v += fmin(-cur_a / cur_v * step, lim_prev - cur_v);
+        lim_t = lim_prev;
+    }
+
+    // forward pass, utils.py:39-63
+    if (v0 == nullptr) {
+        pv(0) = cur_v;
+    } else {
+        cur_v = fmax(v0[b], v_min);
+        pv(0) = cur_v;
+    }
+    if (a0 == nullptr) {
+        cur_a = -cur_a;
+        pa(0) = cur_a;
+    } else {
+        cur_a = a0[b];
+        pa(0) = cur_a;
+    }
+    double lim_a = 0.0;
+    for (int t = 0; t < N; ++t) {
+        const double p_t = pv(t);
+        if (t < N - 1) lim_a = fmin(a_max, (pv(t + 1) - cur_v) / step * cur_v);
+        if (lim_a > 0.0) {
+            cur_a = fmin(cur_a + j_max / cur_v * step, lim_a);
+        } else {
+            cur_a = 0.0;
+            cur_v = p_t;
+        }
+        const double next_v = cur_v + fmin(cur_a / cur_v * step, lim(t) - cur_v);
+        cur_v = fmin(p_t, next_v);
+        pv(t) = cur_v;
+        pa(t) = cur_a;
+    }
+}
+
+// path_optim.py:11-55.  The inner loop looks at every sample ahead of (behind) i, so the
+// problem's `upper` row is staged in shared memory once: s_upper[k][threadIdx.x].
+__global__ void rampify_lateral_kernel(int B, int N, int horizon, double step, double evasion_sharpness,
+                                       const double* __restrict__ proj_distance, const double* __restrict__ path_v,
+                                       double gap, const double* __restrict__ lower, const double* __restrict__ upper,
+                                       double* __restrict__ d_offset) {
+    extern __shared__ double s_upper[];                      // [horizon][blockDim.x]
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int nt = blockDim.x, tx = threadIdx.x;
+    for (int k = 0; k < horizon; ++k) s_upper[k * nt + tx] = upper[(size_t)k * B + b] - gap;
+    auto out = [&](int i) -> double& { return d_offset[(size_t)i * B + b]; };
+    for (int i = 0; i < N; ++i) out(i) = -10.0;               // :21-22
+    const double proj = proj_distance[b];
+
+    for (int pass_nr = 0; pass_nr < 2; ++pass_nr) {
+        double d = pass_nr == 0 ? lower[b] : lower[(size_t)(horizon - 1) * B + b];
+        for (int n = 0; n < horizon; ++n) {
+            const int i = pass_nr == 0 ? n : horizon - 1 - n;
+            d = fmax(lower[(size_t)i * B + b], d);
+            // forward pass writes, backward pass folds with the forward value (np.maximum, :55)
+            out(i) = pass_nr == 0 ? d : fmax(out(i), d);
+            const double v = fmax(path_v[(size_t)i * B + b], 1e-8);
+            double slope = -(evasion_sharpness / (v * v));
+            if (pass_nr == 0) {
+                for (int k = i; k < horizon; ++k)
+                    slope = fmin(slope, (s_upper[k * nt + tx] - d) / (fmax(1.0, (double)(k - i)) * step));
+            } else {
+                for (int k = i; k >= 0; --k)
+                    slope = fmin(slope, (s_upper[k * nt + tx] - d) / (fmax(1.0, (double)(i - k)) * step));
+                slope = fmin(slope, (proj - d) / fmax(1.0, i * step));          // :50-51
+            }
+            d += step * slope;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t tplb_prep_abi_version(void) { return TPLB_PREP_ABI_VERSION; }
+const char* tplb_prep_last_error(void) { return g_error; }
+
+int32_t tplb_rampify_velocity(int32_t batch, int32_t n, const double* v0, const double* a0, const double* lim_v,
+                              double a_min, double a_max, double j_min, double j_max, double v_min, double step,
+                              double* profile, void* stream) {
+    if (batch <= 0 || n <= 0) return fail(TPLB_PREP_E_ARG, "batch and n must be positive");
+    if (!lim_v || !profile) return fail(TPLB_PREP_E_ARG, "lim_v / profile is NULL");
+    const int block = 64;
+    rampify_velocity_kernel<<<(batch + block - 1) / block, block, 0, static_cast<cudaStream_t>(stream)>>>(
+        batch, n, v0, a0, lim_v, a_min, a_max, j_min, j_max, v_min, step, profile);
+    return check_launch("tplb_rampify_velocity");
+}
+
+int32_t tplb_rampify_lateral(int32_t batch, int32_t n, int32_t horizon, double step, double evasion_sharpness,
+                             const double* proj_distance, const double* path_v, double gap, const double* lower,
+                             const double* upper, double* d_offset, void* stream) {
+    if (batch <= 0 || n <= 0) return fail(TPLB_PREP_E_ARG, "batch and n must be positive");
+    if (horizon <= 0 || horizon > n) return fail(TPLB_PREP_E_ARG, "horizon must be in 1..n");
+    if (!proj_distance || !path_v || !lower || !upper || !d_offset) return fail(TPLB_PREP_E_ARG, "NULL array");
+    const int block = 32;
+    const size_t smem = sizeof(double) * (size_t)horizon * block;
+    if (smem > 200 * 1024) return fail(TPLB_PREP_E_ARG, "horizon too long for the shared-memory tile (max 800)");
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(rampify_lateral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured = true;
+    }
+    rampify_lateral_kernel<<<(batch + block - 1) / block, block, smem, static_cast<cudaStream_t>(stream)>>>(
+        batch, n, horizon, step, evasion_sharpness, proj_distance, path_v, gap, lower, upper, d_offset);
+    return check_launch("tplb_rampify_lateral");
+}
+
+}  // extern "C"

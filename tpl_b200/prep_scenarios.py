@@ -1,0 +1,76 @@
+"""Seeded synthetic inputs for the profile-shaping routines (`tpl_b200.prep`): speed-limit
+profiles with steps and curvature dips for the velocity ramp, lateral corridors with obstacle
+bumps for the evasive-offset ramp.  Used by the tests, the golden generator and bench.py, so all
+of them see the same numbers."""
+
+import numpy as np
+
+# planning defaults of the reference's parameter files (data/params/planning/default)
+VELOCITY_DEFAULTS = dict(a_min=-2.5, a_max=1.5, j_min=-1.5, j_max=1.0, v_min=1.0, step=1.0)
+LATERAL_DEFAULTS = dict(step=0.5, evasion_sharpness=4.0, gap=0.3)
+
+
+def velocity_case(seed, n=250, with_v0=True, with_a0=True, **over):
+    rng = np.random.default_rng(seed)
+    p = dict(VELOCITY_DEFAULTS, **over)
+    s = np.arange(n) * p["step"]
+    lim = np.full(n, rng.uniform(8.0, 16.0))
+    for _ in range(rng.integers(1, 4)):                       # speed-limit steps
+        a = rng.integers(10, n - 10)
+        lim[a:] = rng.uniform(3.0, 16.0)
+    kappa = 0.08 * np.sin(s / rng.uniform(12.0, 40.0) + rng.uniform(0, 6.0)) ** 2
+    lim = np.minimum(lim, np.sqrt(2.0 / np.maximum(kappa, 1e-4)))   # lateral-acceleration limit
+    if rng.uniform() < 0.5:                                   # stop point
+        a = rng.integers(n // 2, n - 5)
+        lim[a:a + 5] = 0.0
+    return dict(p, lim_v=lim, v0=float(rng.uniform(0.0, 14.0)) if with_v0 else None,
+                a0=float(rng.uniform(-1.0, 1.0)) if with_a0 else None)
+
+
+def velocity_cases():
+    cases = [velocity_case(100 + i) for i in range(6)]
+    cases.append(velocity_case(200, with_v0=False, with_a0=False))
+    cases.append(velocity_case(201, with_v0=True, with_a0=False))
+    cases.append(velocity_case(202, n=40, step=2.0))
+    cases.append(velocity_case(203, n=300, v_min=0.5))
+    return cases
+
+
+def lateral_case(seed, n=200, horizon=None, **over):
+    rng = np.random.default_rng(seed)
+    p = dict(LATERAL_DEFAULTS, **over)
+    horizon = n if horizon is None else horizon
+    lower = np.full(n, -1.5) + 0.1 * np.sin(np.arange(n) / 9.0 + rng.uniform(0, 6))
+    upper = np.full(n, 1.5) + 0.1 * np.cos(np.arange(n) / 7.0 + rng.uniform(0, 6))
+    for _ in range(rng.integers(1, 3)):                       # obstacles pushing the lower bound up
+        a = rng.integers(20, max(21, horizon - 30))
+        lower[a:a + rng.integers(8, 25)] = rng.uniform(-0.6, 0.5)
+    path = np.zeros((n, 6))
+    path[:, 5] = np.maximum(rng.uniform(2.0, 12.0) + np.cumsum(rng.normal(0, 0.05, n)), 0.0)
+    if rng.uniform() < 0.3:
+        path[rng.integers(0, n), 5] = 0.0                     # exercises the max(v, 1e-8) guard
+    # the reference passes (lower, -upper_constraint) for one side and the mirrored pair for the other
+    return dict(p, horizon=horizon, proj_distance=float(rng.uniform(-0.5, 0.5)), path=path,
+                lower=lower, upper=upper)
+
+
+def lateral_cases():
+    cases = [lateral_case(300 + i) for i in range(6)]
+    cases.append(lateral_case(400, n=250, horizon=200))
+    cases.append(lateral_case(401, n=60, step=1.0))
+    cases.append(lateral_case(402, evasion_sharpness=0.5, gap=0.0))
+    return cases
+
+
+def velocity_batch(batch, n=250, seed0=0):
+    """Arrays for a whole batch: lim_v (B, n), v0 (B,), a0 (B,), shared scalars."""
+    cs = [velocity_case(seed0 + i, n=n) for i in range(batch)]
+    return dict(VELOCITY_DEFAULTS, lim_v=np.stack([c["lim_v"] for c in cs]),
+                v0=np.array([c["v0"] for c in cs]), a0=np.array([c["a0"] for c in cs]))
+
+
+def lateral_batch(batch, n=200, seed0=0):
+    cs = [lateral_case(seed0 + i, n=n) for i in range(batch)]
+    return dict(LATERAL_DEFAULTS, horizon=n, proj_distance=np.array([c["proj_distance"] for c in cs]),
+                path_v=np.stack([c["path"][:, 5] for c in cs]), lower=np.stack([c["lower"] for c in cs]),
+                upper=np.stack([c["upper"] for c in cs]))
