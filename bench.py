@@ -511,6 +511,8 @@ def run_ours(a):
             line["latency"] = single_solve_latency(lib, pb, cpu=True)
             # the same kernels once the batch fills the chip (not the headline workload)
             line["large_batch"] = large_batch_throughput(lib, a, 65536)
+            # row f2: the profile shaping that precedes the lateral / velocity solves
+            line["profile_shaping"] = profile_shaping()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -549,6 +551,57 @@ def single_solve_latency(lib, pb, reps=200, cpu=True):
             rt.append((time.perf_counter() - t0) * 1e3)
         out["cpu_p50_ms"] = float(np.median(rt))
         out["cpu_kind"] = kind
+    return out
+
+
+def profile_shaping(batch=16384, reps=20, cpu_sample=256):
+    """Row f2 (tpl_b200.prep): the two rampify kernels at config #4's batch size, device-resident
+    inputs, CUDA events; beside them the C restatement (oracle) on one host core."""
+    import numpy as np
+    import torch
+    from oracle import prep as oprep
+    from tpl_b200 import prep, prep_scenarios as ps
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = {}
+    vb = ps.velocity_batch(64, n=250)
+    tile = lambda x: torch.as_tensor(np.resize(x, (batch,) + x.shape[1:]), device=dev)   # noqa: E731
+    lim, v0, a0 = tile(vb["lim_v"]), tile(vb["v0"]), tile(vb["a0"])
+    args = (vb["a_min"], vb["a_max"], vb["j_min"], vb["j_max"], vb["v_min"], vb["step"])
+    lb = ps.lateral_batch(64, n=200)
+    pv, lo, up, pj = tile(lb["path_v"]), tile(lb["lower"]), tile(lb["upper"]), tile(lb["proj_distance"])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms = timed(lambda: prep.rampify_velocity_profile(v0, a0, lim, *args))
+    t0 = time.perf_counter()
+    for k in range(cpu_sample):
+        oprep.rampify_velocity(vb["v0"][k % 64], vb["a0"][k % 64], vb["lim_v"][k % 64], *args)
+    cpu = cpu_sample / (time.perf_counter() - t0)
+    out["velocity"] = {"problems": batch, "samples": 250, "ms": ms, "profiles_per_s": batch / (ms * 1e-3),
+                       "cpu_port_profiles_per_s_1core": cpu,
+                       "what": "includes the (B,N)->[N][B] transposes of the wrapper"}
+    ms = timed(lambda: prep.rampify_lateral_profile(lb["step"], 200, lb["evasion_sharpness"], pj, pv, lb["gap"], lo, up))
+    path = np.zeros((200, 6))
+    t0 = time.perf_counter()
+    for k in range(cpu_sample):
+        path[:, 5] = lb["path_v"][k % 64]
+        oprep.rampify_lateral(lb["step"], 200, lb["evasion_sharpness"], lb["proj_distance"][k % 64], path, lb["gap"],
+                              lb["lower"][k % 64], lb["upper"][k % 64])
+    cpu = cpu_sample / (time.perf_counter() - t0)
+    out["lateral"] = {"problems": batch, "samples": 200, "ms": ms, "profiles_per_s": batch / (ms * 1e-3),
+                      "cpu_port_profiles_per_s_1core": cpu,
+                      "divisions_per_profile": 2 * 200 * 201 // 2 + 200}
     return out
 
 
