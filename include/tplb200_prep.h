@@ -52,6 +52,18 @@ TPLB_PREP_API int32_t tplb_rampify_lateral(int32_t batch, int32_t n, int32_t hor
                                            const double* path_v, double gap, const double* lower,
                                            const double* upper, double* d_offset, void* stream);
 
+/* Warm start between planning cycles: resample a trajectory array on its own uniform grid
+ * ss = i*step at ss + offset[b] (the arc length travelled since the last cycle).  Replaces
+ * VelocityOptim.shift_interp = scipy.interpolate.interp1d(ss, arr, kind, axis=0,
+ * fill_value="extrapolate")(ss + arc_len), planning/path_vel_decomp/velocity_optim.py:86-104,
+ * applied to opt.x[:-1], opt.u and opt.lagrange_multiplier at :163-168 (scipy 1.x: `linear` =
+ * searchsorted + two-point formula with linear extrapolation, `zero` = previous sample, clamped).
+ * in, out: [n][rows][B] (the solver's layout for x, u, lambda); must not overlap. */
+enum { TPLB_INTERP_LINEAR = 0, TPLB_INTERP_ZERO = 1 };
+TPLB_PREP_API int32_t tplb_shift_interp(int32_t batch, int32_t n, int32_t rows, double step,
+                                        const double* offset, int32_t kind, const double* in, double* out,
+                                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,3 +57,24 @@ def rampify_lateral(step, horizon, evasion_sharpness, proj_distance, path, gap, 
     lib().tplo_rampify_lateral(n, int(horizon), step, evasion_sharpness, float(proj_distance), path_v, gap,
                                lower, upper, fwd, bwd, out)
     return out
+
+
+def shift_interp(arr, step, arc_len, kind="linear"):
+    """VelocityOptim.shift_interp (planning/path_vel_decomp/velocity_optim.py:86-104) for one
+    problem: scipy.interpolate.interp1d(ss, arr, kind, axis=0, fill_value="extrapolate")(ss + arc_len)
+    with ss = arange(0, n*step, step).  scipy (unpinned in library/setup.py:108, 1.18.1 here) is not
+    imported; this restates its published algorithm: `linear` = numpy.searchsorted (side left),
+    indices clipped to 1..n-1, slope*(x_new - x_lo) + y_lo; `zero` = the previous sample, held
+    constant beyond both ends."""
+    arr = np.asarray(arr, dtype=np.float64)
+    n = arr.shape[0]
+    ss = np.arange(n) * float(step)
+    xq = ss + float(arc_len)
+    if kind == "zero":
+        idx = np.clip(np.searchsorted(ss, xq, side="right") - 1, 0, n - 1)
+        return arr[idx]
+    hi = np.clip(np.searchsorted(ss, xq), 1, n - 1)
+    lo = hi - 1
+    shape = (-1,) + (1,) * (arr.ndim - 1)
+    slope = (arr[hi] - arr[lo]) / (ss[hi] - ss[lo]).reshape(shape)
+    return slope * (xq - ss[lo]).reshape(shape) + arr[lo]

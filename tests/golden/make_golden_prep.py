@@ -43,7 +43,37 @@ def reference_function(path, name):
     return ns[name]
 
 
+def reference_method(path, cls, name, extra):
+    """Method `name` of class `cls` in the reference file `path`, as a plain function."""
+    import textwrap
+    src = open(path).read()
+    tree = ast.parse(src)
+    c = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls)
+    node = next(n for n in c.body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = dict(extra)
+    exec(compile(textwrap.dedent(ast.get_source_segment(src, node, padded=True)), path, "exec"), ns)
+    return ns[name]
+
+
+def shift_interp_golden():
+    """VelocityOptim.shift_interp (velocity_optim.py:98-104) run as it stands, with scipy's interp1d."""
+    from types import SimpleNamespace
+    from scipy.interpolate import interp1d
+    fn = reference_method(os.path.join(REF, "planning", "path_vel_decomp", "velocity_optim.py"),
+                          "VelocityOptim", "shift_interp", {"interp1d": interp1d, "np": np})
+    out = {}
+    for i, c in enumerate(ps.shift_cases()):
+        n = c["arr"].shape[0]
+        me = SimpleNamespace(ss=np.arange(0.0, n * c["step"], c["step"])[:n])      # update_shifts, :88
+        me.shifts = me.ss + c["arc_len"]                                          # :92
+        out[f"linear_{i}"] = fn(me, c["arr"])
+        out[f"zero_{i}"] = fn(me, c["arr"], interp_kind="zero")
+    np.savez_compressed(os.path.join(HERE, "prep_shift_interp.npz"), **out)
+    print("shift_interp:", len(ps.shift_cases()), "cases")
+
+
 def main():
+    shift_interp_golden()
     vel = reference_function(os.path.join(REF, "planning", "utils.py"), "rampify_profile")
     lat = reference_function(os.path.join(REF, "planning", "path_vel_decomp", "path_optim.py"), "rampify_profile")
 

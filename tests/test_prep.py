@@ -132,3 +132,63 @@ def test_shaped_corridor_feeds_the_lateral_solver(prep_lib, solver_libs):
     opt.update()
     torch.cuda.synchronize()
     assert bool(torch.isfinite(opt.traj_costs).all())
+
+
+def test_shift_interp_oracle_matches_scipy_golden():
+    """The golden file holds what the reference's VelocityOptim.shift_interp returns (scipy interp1d)."""
+    g = np.load(os.path.join(GOLDEN, "prep_shift_interp.npz"))
+    for i, c in enumerate(ps.shift_cases()):
+        for kind in ("linear", "zero"):
+            np.testing.assert_allclose(oprep.shift_interp(c["arr"], c["step"], c["arc_len"], kind), g[f"{kind}_{i}"],
+                                       rtol=RTOL, atol=1e-11)
+
+
+@pytest.mark.gpu
+def test_shift_interp_matches_golden_and_oracle(prep_lib):
+    g = np.load(os.path.join(GOLDEN, "prep_shift_interp.npz"))
+    for i, c in enumerate(ps.shift_cases()):
+        for kind in ("linear", "zero"):
+            out = prep.shift_interp(c["arr"][None], c["step"], [c["arc_len"]], kind)
+            assert out.shape == (1,) + c["arr"].shape
+            np.testing.assert_allclose(out[0].cpu().numpy(), g[f"{kind}_{i}"], rtol=RTOL, atol=1e-11)
+    # a batch with a different travelled distance per problem
+    rng = np.random.default_rng(77)
+    B, n, rows, step = 300, 120, 3, 0.5
+    arr = np.cumsum(rng.normal(0, 1, (B, n, rows)), axis=1)
+    arc = rng.uniform(-1.0, 8.0, B)
+    arc[:4] = [0.0, 0.5, 1.0, 59.5]                              # exact grid points
+    for kind in ("linear", "zero"):
+        out = prep.shift_interp(arr, step, arc, kind).cpu().numpy()
+        for k in range(0, B, 3):
+            np.testing.assert_allclose(out[k], oprep.shift_interp(arr[k], step, arc[k], kind), rtol=RTOL, atol=1e-11)
+    out1 = prep.shift_interp(arr[:, :, 0], step, arc, "zero")     # (B, n) input keeps its shape
+    assert out1.shape == (B, n)
+
+
+@pytest.mark.gpu
+def test_solver_warm_start_resampling(prep_lib, solver_libs):
+    """velocity_optim.py:163-168 on the solver's own buffers: x[:-1] and the multipliers linear, u
+    zero-order, x[T] untouched; then the solve runs from the shifted warm start."""
+    from tpl_b200 import scenarios as sc
+    from tpl_b200.batched import BatchedOptim
+    B, T = 48, 150
+    pb = sc.velocity(batch=B, horizon=T, max_iterations=8, seed0=31)
+    opt = sc.apply_to_batched(BatchedOptim(solver_libs[pb.model], batch=B, scenes=pb.scenes, horizon_max=T), pb)
+    opt.update()
+    x, u, lam = (t.cpu().numpy().copy() for t in (opt.x, opt.u, opt.lagrange_multiplier))
+    arc = np.random.default_rng(5).uniform(0.0, 3.0, B)
+    opt.shift_interp(arc)
+    torch.cuda.synchronize()
+    x2, u2, lam2 = (t.cpu().numpy() for t in (opt.x, opt.u, opt.lagrange_multiplier))
+    step = opt.dt
+    for k in range(0, B, 5):
+        np.testing.assert_allclose(x2[k, :T].reshape(T, -1), oprep.shift_interp(x[k, :T].reshape(T, -1), step, arc[k]),
+                                   rtol=RTOL, atol=1e-11)
+        np.testing.assert_array_equal(x2[k, T], x[k, T])
+        np.testing.assert_array_equal(u2[k].reshape(T, -1),
+                                      oprep.shift_interp(u[k].reshape(T, -1), step, arc[k], "zero"))
+        np.testing.assert_allclose(lam2[k].reshape(T, -1), oprep.shift_interp(lam[k].reshape(T, -1), step, arc[k]),
+                                   rtol=RTOL, atol=1e-11)
+    opt.update()
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(opt.traj_costs).all())

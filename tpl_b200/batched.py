@@ -26,6 +26,8 @@ device and the sm_100a library loaded.
 import copy as _copy
 import ctypes as C
 
+import contextlib
+
 import numpy as np
 import torch
 
@@ -515,6 +517,21 @@ class BatchedOptim:
 
     def ct_dynamics(self, x, u, t, dt):
         return self._points(x, u, t, dt, 1)
+
+    def shift_interp(self, arc_len):
+        """Warm start between planning cycles (velocity_optim.py:163-168): ``x[:-1]`` and the
+        multipliers are resampled linearly, ``u`` with a zero-order hold, at ``ss + arc_len`` on the
+        grid ``ss = i * step`` — per problem ``arc_len`` of shape (B,).  On the device, in place."""
+        from . import prep
+        T = self._T
+        with torch.cuda.device(self.device) if self.device.type == "cuda" else contextlib.nullcontext():
+            if self.device.type != "cuda":
+                raise _cabi.SolverError("shift_interp runs on a CUDA device only; there is no CPU fallback")
+            self._x[:T].copy_(prep.shift_interp_soa(self._x[:T], self.dt, arc_len, "linear"))
+            self._u[:T].copy_(prep.shift_interp_soa(self._u[:T], self.dt, arc_len, "zero"))
+            if self.C:
+                lam = self._lam[:T]
+                lam.copy_(prep.shift_interp_soa(lam, self.dt, arc_len, "linear"))
 
     def argmin_groups(self, per_group):
         """Multi-start reduction: best finite ``traj_costs`` of each contiguous

@@ -121,6 +121,38 @@ __global__ void rampify_lateral_kernel(int B, int N, int horizon, double step, d
     }
 }
 
+// velocity_optim.py:98-104 through scipy's interp1d.  Grid and query points are formed exactly
+// as numpy does (ss[i] = i*step, then + offset: two roundings, no FMA) because they decide
+// which interval a query falls into.
+__global__ void shift_interp_kernel(int B, int n, int rows, double step, const double* __restrict__ offset,
+                                    int kind, const double* __restrict__ in, double* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (b >= B) return;
+    auto grid = [&](int j) { return __dmul_rn((double)j, step); };
+    const double xq = __dadd_rn(grid(i), offset[b]);
+    // first j with grid(j) >= xq (numpy.searchsorted, side = left), from a guess
+    int j = (int)ceil(xq / step);
+    j = j < 0 ? 0 : (j > n ? n : j);
+    while (j > 0 && grid(j - 1) >= xq) --j;
+    while (j < n && grid(j) < xq) ++j;
+    if (kind == TPLB_INTERP_ZERO) {
+        // previous sample: last j' with grid(j') <= xq, clamped to the ends
+        int p = (j < n && grid(j) == xq) ? j : j - 1;
+        p = p < 0 ? 0 : (p > n - 1 ? n - 1 : p);
+        for (int r = 0; r < rows; ++r)
+            out[((size_t)i * rows + r) * B + b] = in[((size_t)p * rows + r) * B + b];
+        return;
+    }
+    const int hi = j < 1 ? 1 : (j > n - 1 ? n - 1 : j), lo = hi - 1;
+    const double x_lo = grid(lo), dx = __dadd_rn(grid(hi), -x_lo), w = __dadd_rn(xq, -x_lo);
+    for (int r = 0; r < rows; ++r) {
+        const double y_lo = in[((size_t)lo * rows + r) * B + b], y_hi = in[((size_t)hi * rows + r) * B + b];
+        const double slope = __ddiv_rn(__dadd_rn(y_hi, -y_lo), dx);
+        out[((size_t)i * rows + r) * B + b] = __dadd_rn(__dmul_rn(slope, w), y_lo);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -156,6 +188,18 @@ int32_t tplb_rampify_lateral(int32_t batch, int32_t n, int32_t horizon, double s
     rampify_lateral_kernel<<<(batch + block - 1) / block, block, smem, static_cast<cudaStream_t>(stream)>>>(
         batch, n, horizon, step, evasion_sharpness, proj_distance, path_v, gap, lower, upper, d_offset);
     return check_launch("tplb_rampify_lateral");
+}
+
+int32_t tplb_shift_interp(int32_t batch, int32_t n, int32_t rows, double step, const double* offset, int32_t kind,
+                          const double* in, double* out, void* stream) {
+    if (batch <= 0 || n < 2 || rows <= 0) return fail(TPLB_PREP_E_ARG, "batch, rows must be positive and n >= 2");
+    if (!(step > 0.0)) return fail(TPLB_PREP_E_ARG, "step must be positive");
+    if (kind != TPLB_INTERP_LINEAR && kind != TPLB_INTERP_ZERO) return fail(TPLB_PREP_E_ARG, "unknown kind");
+    if (!offset || !in || !out || in == out) return fail(TPLB_PREP_E_ARG, "NULL or aliased array");
+    const int block = 128;
+    shift_interp_kernel<<<dim3((batch + block - 1) / block, n), block, 0, static_cast<cudaStream_t>(stream)>>>(
+        batch, n, rows, step, offset, kind, in, out);
+    return check_launch("tplb_shift_interp");
 }
 
 }  // extern "C"

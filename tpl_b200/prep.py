@@ -10,6 +10,13 @@ on the GPU through the C ABI of ``include/tplb200_prep.h``.
         path (B, N, >=6) (column 5 is used) or (B, N) = that column, lower / upper (B, N),
         proj_distance (B,)  ->  d_offset (B, N)
 
+    shift_interp(arr, step, arc_len, kind="linear")
+        reference: VelocityOptim.shift_interp (planning/path_vel_decomp/velocity_optim.py:86-104), i.e.
+        scipy interp1d(ss, arr, kind, axis=0, fill_value="extrapolate")(ss + arc_len) with ss = i*step;
+        arr (B, n) or (B, n, rows), arc_len (B,)  ->  same shape as arr
+    shift_interp_soa(buf, step, arc_len, kind)
+        the same on a solver buffer [n][rows][B] (no transposes; used by BatchedOptim.shift_interp)
+
 There is no CPU fallback: the calls raise without the CUDA library or a CUDA device."""
 
 import ctypes as C
@@ -19,7 +26,9 @@ import numpy as np
 import torch
 
 _D = C.c_void_p
-EXPORTS = ("tplb_prep_abi_version", "tplb_prep_last_error", "tplb_rampify_velocity", "tplb_rampify_lateral")
+EXPORTS = ("tplb_prep_abi_version", "tplb_prep_last_error", "tplb_rampify_velocity", "tplb_rampify_lateral",
+           "tplb_shift_interp")
+KINDS = {"linear": 0, "zero": 1}
 ABI_VERSION = 1
 
 
@@ -50,6 +59,8 @@ def load(path=None):
     lib.tplb_rampify_lateral.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, _D, _D,
                                          C.c_double, _D, _D, _D, C.c_void_p]
     lib.tplb_rampify_lateral.restype = C.c_int32
+    lib.tplb_shift_interp.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_double, _D, C.c_int32, _D, _D, C.c_void_p]
+    lib.tplb_shift_interp.restype = C.c_int32
     if lib.tplb_prep_abi_version() != ABI_VERSION:
         raise PrepError(f"{path}: ABI version {lib.tplb_prep_abi_version()} != {ABI_VERSION}")
     _LIB = lib
@@ -125,3 +136,32 @@ def rampify_lateral_profile(step, horizon, evasion_sharpness, proj_distance, pat
                                       out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
         _check(lib, rc, "tplb_rampify_lateral")
     return out.t()
+
+
+def shift_interp_soa(buf, step, arc_len, kind="linear"):
+    """``buf``: contiguous CUDA tensor [n][rows][B] -> new tensor of the same shape."""
+    lib = load()
+    if not (isinstance(buf, torch.Tensor) and buf.is_cuda and buf.is_contiguous() and buf.ndim == 3
+            and buf.dtype == torch.float64):
+        raise PrepError("shift_interp_soa needs a contiguous fp64 CUDA tensor [n][rows][B]")
+    n, rows, batch = buf.shape
+    with torch.cuda.device(buf.device):
+        off = _per_problem(arc_len, buf.device, batch, "arc_len")
+        out = torch.empty_like(buf)
+        rc = lib.tplb_shift_interp(batch, n, rows, float(step), off.data_ptr(), KINDS[kind], buf.data_ptr(),
+                                   out.data_ptr(), torch.cuda.current_stream(buf.device).cuda_stream)
+        _check(lib, rc, "tplb_shift_interp")
+    return out
+
+
+def shift_interp(arr, step, arc_len, kind="linear", device=None):
+    dev = _device(device)
+    t = arr if isinstance(arr, torch.Tensor) else torch.as_tensor(np.asarray(arr, dtype=np.float64))
+    t = t.to(device=dev, dtype=torch.float64, non_blocking=True)
+    squeeze = t.ndim == 2
+    if squeeze:
+        t = t.unsqueeze(-1)
+    if t.ndim != 3:
+        raise ValueError(f'Expected "arr" with shape (B, n) or (B, n, rows), but found {tuple(t.shape)}')
+    out = shift_interp_soa(t.permute(1, 2, 0).contiguous(), step, arc_len, kind).permute(2, 0, 1)
+    return out.squeeze(-1) if squeeze else out

@@ -74,3 +74,16 @@ def lateral_batch(batch, n=200, seed0=0):
     return dict(LATERAL_DEFAULTS, horizon=n, proj_distance=np.array([c["proj_distance"] for c in cs]),
                 path_v=np.stack([c["path"][:, 5] for c in cs]), lower=np.stack([c["lower"] for c in cs]),
                 upper=np.stack([c["upper"] for c in cs]))
+
+
+def shift_cases():
+    """Trajectory arrays (n, rows) with the arc length travelled since the last cycle: inside the
+    grid, beyond its end (extrapolation), backwards, exact multiples of the step, zero."""
+    cases = []
+    for i, (n, rows, step, arc) in enumerate([(250, 3, 1.0, 0.37), (250, 1, 0.5, 2.5), (100, 2, 0.3, 0.9),
+                                              (60, 4, 2.0, -0.8), (40, 2, 0.1, 7.3), (250, 5, 1.0, 0.0),
+                                              (30, 1, 0.7, 30.0), (120, 2, 0.25, 1e-9)]):
+        rng = np.random.default_rng(800 + i)
+        arr = np.cumsum(rng.normal(0.0, 1.0, (n, rows)), axis=0) + rng.uniform(-5, 5)
+        cases.append(dict(arr=arr, step=step, arc_len=arc))
+    return cases
