@@ -3,6 +3,7 @@
 
     python scripts/summarize_ncu.py launches gpurun_out/launches.csv > profiles/rNN_launches.md
     python scripts/summarize_ncu.py kernels  gpurun_out/prof.ncu-rep > profiles/rNN_kernels.md
+    python scripts/summarize_ncu.py metrics  gpurun_out/ncu.csv      > profiles/rNN_ncu.md
 """
 import collections
 import csv
@@ -78,5 +79,28 @@ def kernels(path):
         print()
 
 
+def metrics(path):
+    """One table for a `ncu --metrics ... --csv --page raw --log-file` capture (one row per launch)."""
+    rows = list(csv.reader(open(path)))
+    h = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    hdr, units = rows[h], rows[h + 1]
+    ki = hdr.index("Kernel Name")
+    cols = [(k, lab) for k, lab in KEEP if k in hdr]
+    print("| # | kernel | " + " | ".join(lab for _, lab in cols) + " |")
+    print("|---:|---|" + "---:|" * len(cols))
+    for n, r in enumerate(rows[h + 2:]):
+        if len(r) < len(hdr):
+            continue
+        vals = []
+        for k, _ in cols:
+            i = hdr.index(k)
+            try:
+                v = float(r[i].replace(",", ""))
+                vals.append((f"{v:,.0f}" if abs(v) >= 1000 else f"{v:.2f}") + (f" {units[i]}" if units[i] not in ("", "%", "inst", "register/thread") else ""))
+            except ValueError:
+                vals.append(r[i])
+        print(f"| {n} | `{short(r[ki]).split('<')[0]}` | " + " | ".join(vals) + " |")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernels": kernels}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "kernels": kernels, "metrics": metrics}[sys.argv[1]](sys.argv[2])
