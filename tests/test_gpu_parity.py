@@ -19,19 +19,27 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-def _factory(solver_libs, pb, **kw):
+def _factory(solver_libs, pb, rounds=0, **kw):
+    """`rounds`: tplb_batch.line_search_rounds — 0/1 run the launch sequence for latency-bound
+    batches at these sizes, 2 the sequence for a full GPU (two-round rollouts that sum their own
+    stage costs, separate accept); both must reproduce the reference."""
     from tpl_b200.batched import BatchedOptim
-    return lambda: BatchedOptim(solver_libs[pb.model], batch=pb.batch, scenes=pb.scenes,
-                                horizon_max=pb.horizon, **kw)
+
+    def make():
+        o = BatchedOptim(solver_libs[pb.model], batch=pb.batch, scenes=pb.scenes, horizon_max=pb.horizon, **kw)
+        o.line_search_rounds = rounds
+        return o
+    return make
 
 
+@pytest.mark.parametrize("rounds", [0, 2])
 @pytest.mark.parametrize("case", list(common.CASES))
-def test_cuda_matches_reference_golden(case, solver_libs):
+def test_cuda_matches_reference_golden(case, rounds, solver_libs):
     pb, iters, _ = common.make_case(case)
     golden, golden_derivs = common.load_golden(case)
     tol = common.LOOSE.get(case, common.RTOL)
-    tr = common.trace_batched(_factory(solver_libs, pb), pb, iters)
-    d = common.derivatives_batched(_factory(solver_libs, pb), pb)
+    tr = common.trace_batched(_factory(solver_libs, pb, rounds), pb, iters)
+    d = common.derivatives_batched(_factory(solver_libs, pb, rounds), pb)
     for i in range(pb.batch):
         worst, flip, plateau = common.compare_traces(common.batched_problem_trace(tr, i), golden[i])
         assert worst <= tol, f"{case} problem {i}: relative error {worst:.3e}"
@@ -47,12 +55,13 @@ def test_cuda_matches_reference_golden(case, solver_libs):
     ("velocity", dict(batch=32, horizon=250, max_iterations=20, forced=False, seed0=3000)),
     ("smoother", dict(batch=32, horizon=250, max_iterations=5, forced=False, seed0=4000)),
 ])
-def test_cuda_matches_oracle_default_mode(model, kw, solver_libs, oracle_libs):
+@pytest.mark.parametrize("rounds", [0, 2])
+def test_cuda_matches_oracle_default_mode(model, kw, rounds, solver_libs, oracle_libs):
     """Final solutions of a larger seeded batch against the CPU oracle:
     identical iteration counts and termination flags, 1e-9 on x, u, cost."""
     from tpl_b200 import scenarios as sc
     pb = getattr(sc, model)(**kw)
-    q = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
+    q = sc.apply_to_batched(_factory(solver_libs, pb, rounds)(), pb)
     q.update()
     X = q.x.cpu().numpy().reshape(pb.batch, pb.horizon + 1, -1)
     U = q.u.cpu().numpy().reshape(pb.batch, pb.horizon, -1)

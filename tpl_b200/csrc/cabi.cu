@@ -173,11 +173,8 @@ void launch_rollout(const tplb_batch& q, const tplb::Workspace& ws, cudaStream_t
 #define TPLB_ROLLOUT_K(SCHEME, MINB)                                                                  \
     do {                                                                                              \
         auto kern = tplb::rollout_kernel<Model, R, PB, kInit, SCHEME, MINB, kCost>;                           \
-        static bool configured = false;                                                               \
-        if (!configured) {                                                                            \
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);      \
-            configured = true;                                                                        \
-        }                                                                                             \
+        if (smem > 48 * 1024)   /* opt in per launch: the attribute belongs to the current device */ \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
         kern<<<grid, block, smem, st>>>(q, ws, a_begin, list);                                        \
     } while (0)
 #define TPLB_ROLLOUT(SCHEME)                                          \

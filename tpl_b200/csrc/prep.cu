@@ -180,11 +180,8 @@ int32_t tplb_rampify_lateral(int32_t batch, int32_t n, int32_t horizon, double s
     const int block = 32;
     const size_t smem = sizeof(double) * (size_t)horizon * block;
     if (smem > 200 * 1024) return fail(TPLB_PREP_E_ARG, "horizon too long for the shared-memory tile (max 800)");
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(rampify_lateral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        configured = true;
-    }
+    if (smem > 48 * 1024)       // opt in per launch: the attribute belongs to the current device
+        cudaFuncSetAttribute(rampify_lateral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     rampify_lateral_kernel<<<(batch + block - 1) / block, block, smem, static_cast<cudaStream_t>(stream)>>>(
         batch, n, horizon, step, evasion_sharpness, proj_distance, path_v, gap, lower, upper, d_offset);
     return check_launch("tplb_rampify_lateral");

@@ -5,9 +5,10 @@
 //
 //   stage_constants_kernel  per-(scene, stage) interpolation lookups, once per update()
 //   rollout_kernel<Init>    optim.c:1096-1107    x[t+1] = F(x[t], u[t])            [problem parallel]
-//   rollout_kernel<Search>  optim.c:732-775      8 step sizes alpha_i = 10^-i at once:
-//                                                u' = clip(u + alpha k + K (x' - x)), x' = F(x', u')
-//   stage_cost_kernel       optim.c:776-789, 1105-1111   cost terms of every (candidate, stage)
+//   rollout_kernel<Search>  optim.c:732-775      step sizes alpha_i = 10^-i side by side:
+//                                                u' = clip(u + alpha k + K (x' - x)), x' = F(x', u');
+//                                                <kCost> also adds up the stage costs (:776-789)
+//   stage_cost*_kernel      optim.c:776-789, 1105-1111   cost terms of every (candidate, stage)
 //                                                                                   [stage parallel]
 //   init_cost_kernel        optim.c:1106-1111    ordered sum -> trajCosts
 //   multiplier_kernel       optim.c:1115-1136    multiplier update, outer-iteration reset
@@ -18,8 +19,13 @@
 //                                                looks at alpha = 1, 0.1; only problems where both
 //                                                fail go to round 2 (alpha = 1e-2 .. 1e-7)
 //   accept_kernel           optim.c:844-848      copy the winning candidate         [stage parallel]
-//                                                (folded into the next linearize_kernel inside the loop)
+//                                                (folded into the next linearize_kernel while
+//                                                launches are latency-bound)
 //   finalize_kernel         optim.c:1145-1149    termination flag
+//
+// cabi.cu strings them together in one of two sequences with identical results: one for a
+// batch that cannot fill the GPU (fewest launches, all 8 step sizes rolled out at once) and
+// one for a full GPU (fewest bytes: two-round rollouts that sum their own costs).
 //
 // Data layout: structure of arrays, problem index fastest — a warp of consecutive
 // problems reads/writes 256 contiguous bytes for every (stage, component).
