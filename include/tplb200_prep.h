@@ -64,6 +64,27 @@ TPLB_PREP_API int32_t tplb_shift_interp(int32_t batch, int32_t n, int32_t rows, 
                                         const double* offset, int32_t kind, const double* in, double* out,
                                         void* stream);
 
+/* Closed-loop simulator step of the ego vehicle for B vehicles at once: SimCore.update_ego
+ * (library/tpl/simulation/core.py:91-134) — actuator dead time (the command applied now is the
+ * oldest buffered one not older than the dead time), kinematic bicycle with characteristic
+ * velocity, explicit Euler, util.normalize_angle (util.py:92-100), clamps.
+ * State and command arrays are [B]; the command histories are [capacity][B] with a length per
+ * vehicle, capacity >= floor(dead_time / dt) + 2. */
+typedef struct {
+    int32_t struct_bytes;
+    int32_t batch;
+    int32_t capacity;              /* rows of the history buffers */
+    int32_t reserved0;
+    double* x; double* y; double* yaw; double* v; double* a; double* steer_angle;     /* ego.* (in/out) */
+    const double* control_acc;     /* ego.control_acc   */
+    const double* control_steer;   /* ego.control_steer */
+    double acc_dead_time, steer_dead_time, wheel_base, v_ch, max_v, min_v, max_steer_angle;
+    double* acc_t; double* acc_value; int32_t* acc_len;            /* self.acc_buffer            */
+    double* steer_t; double* steer_value; int32_t* steer_len;      /* self.steering_angle_buffer */
+} tplb_ego;
+
+TPLB_PREP_API int32_t tplb_update_ego(const tplb_ego* ego, double t, double dt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

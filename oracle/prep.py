@@ -78,3 +78,37 @@ def shift_interp(arr, step, arc_len, kind="linear"):
     shape = (-1,) + (1,) * (arr.ndim - 1)
     slope = (arr[hi] - arr[lo]) / (ss[hi] - ss[lo]).reshape(shape)
     return slope * (xq - ss[lo]).reshape(shape) + arr[lo]
+
+
+class _Ego(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("x", "y", "yaw", "v", "a", "steer_angle", "control_acc", "control_steer",
+                                          "acc_dead_time", "steer_dead_time", "wheel_base", "v_ch", "max_v",
+                                          "min_v", "max_steer_angle")]
+
+
+class _History(C.Structure):
+    _fields_ = [("len", C.c_int), ("t", C.c_double * 64), ("value", C.c_double * 64)]
+
+
+class EgoOracle:
+    """SimCore.update_ego (simulation/core.py:91-134) for one vehicle; attribute names of the
+    reference's `ego` object."""
+
+    def __init__(self, **kw):
+        object.__setattr__(self, "_e", _Ego())
+        object.__setattr__(self, "_acc", _History())
+        object.__setattr__(self, "_steer", _History())
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    def __getattr__(self, n):
+        return getattr(self._e, n)
+
+    def __setattr__(self, n, v):
+        setattr(self._e, n, float(v))
+
+    def update(self, t, dt):
+        fn = lib().tplo_update_ego
+        fn.argtypes = [C.POINTER(_Ego), C.POINTER(_History), C.POINTER(_History), C.c_double, C.c_double]
+        fn.restype = None
+        fn(C.byref(self._e), C.byref(self._acc), C.byref(self._steer), float(t), float(dt))

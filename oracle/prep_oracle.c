@@ -88,3 +88,66 @@ void tplo_rampify_lateral(int n, int horizon, double step, double evasion_sharpn
     }
     for (int i = 0; i < n; ++i) out[i] = dmax(fwd[i], bwd[i]);     /* :55 */
 }
+
+/* ---- SimCore.update_ego, library/tpl/simulation/core.py:91-134, one vehicle ------------------- */
+
+typedef struct {
+    double x, y, yaw, v, a, steer_angle, control_acc, control_steer;
+    double acc_dead_time, steer_dead_time, wheel_base, v_ch, max_v, min_v, max_steer_angle;
+} tplo_ego;
+
+/* a command history: the reference's Python list of (t, value) */
+typedef struct {
+    int len;
+    double t[64], value[64];
+} tplo_history;
+
+/* Python float floor division (CPython floatobject.c float_divmod) */
+static double floordiv(double a, double b) {
+    double mod = fmod(a, b), div = (a - mod) / b;
+    if (mod != 0.0 && ((b < 0) != (mod < 0))) div -= 1.0;
+    if (div == 0.0) return copysign(0.0, a / b);
+    double f = floor(div);
+    return (div - f > 0.5) ? f + 1.0 : f;
+}
+
+static double pymod(double a, double m) {
+    double r = fmod(a, m);
+    if (r != 0.0 && ((r < 0) != (m < 0))) r += m;
+    return r;
+}
+
+static void history_step(tplo_history* h, double t, double dt, double command, double dead_time, double* applied) {
+    if (dt > 0.0) {                                                /* core.py:95-102 */
+        h->t[h->len] = t;
+        h->value[h->len] = command;
+        h->len++;
+        while (h->len > floordiv(dead_time, dt) + 1) {
+            for (int i = 1; i < h->len; ++i) { h->t[i - 1] = h->t[i]; h->value[i - 1] = h->value[i]; }
+            h->len--;
+        }
+    }
+    if (dead_time == 0.0 && h->len > 0) {                          /* :104-110 */
+        *applied = h->value[h->len - 1];
+    } else {
+        for (int i = 0; i < h->len; ++i)
+            if (t - h->t[i] <= dead_time) { *applied = h->value[i]; break; }
+    }
+}
+
+void tplo_update_ego(tplo_ego* e, tplo_history* acc, tplo_history* steer, double t, double dt) {
+    const double pi = 3.141592653589793;
+    history_step(acc, t, dt, e->control_acc, e->acc_dead_time, &e->a);
+    history_step(steer, t, dt, e->control_steer, e->steer_dead_time, &e->steer_angle);
+    e->x += dt * e->v * cos(e->yaw);                               /* :122-123 */
+    e->y += dt * e->v * sin(e->yaw);
+    double r = e->v / e->v_ch;
+    e->yaw += dt * e->v / (e->wheel_base * (1 + r * r)) * tan(e->steer_angle);   /* :125-126 */
+    double a = pymod(e->yaw, pi * 2);                              /* util.py:95-98 */
+    a = pymod(a + pi * 2, pi * 2);
+    if (a > pi) a -= pi * 2;
+    e->yaw = a;
+    e->v += dt * e->a;                                             /* :130-131 */
+    e->v = fmin(e->max_v, fmax(e->min_v, e->v));
+    e->steer_angle = fmin(e->max_steer_angle, fmax(-e->max_steer_angle, e->steer_angle));
+}

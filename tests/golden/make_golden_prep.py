@@ -72,8 +72,31 @@ def shift_interp_golden():
     print("shift_interp:", len(ps.shift_cases()), "cases")
 
 
+def update_ego_golden():
+    """SimCore.update_ego (simulation/core.py:91-134) run as it stands: the method is taken from the
+    reference file, `util.normalize_angle` from the reference's util.py (numba), `self` and `ego`
+    are plain namespaces with the attributes the method touches."""
+    from types import SimpleNamespace
+    norm = reference_function(os.path.join(REF, "util.py"), "normalize_angle")
+    fn = reference_method(os.path.join(REF, "simulation", "core.py"), "SimCore", "update_ego",
+                          {"np": np, "util": SimpleNamespace(normalize_angle=norm)})
+    out = {}
+    for i, c in enumerate(ps.ego_cases()):
+        me = SimpleNamespace(acc_buffer=[], steering_angle_buffer=[])
+        ego = SimpleNamespace(**c["params"], **c["init"], control_acc=0.0, control_steer=0.0)
+        rows = []
+        for k in range(len(c["control_acc"])):
+            ego.control_acc, ego.control_steer = float(c["control_acc"][k]), float(c["control_steer"][k])
+            fn(me, ego, k * c["dt"], c["dt"])
+            rows.append([ego.x, ego.y, ego.yaw, ego.v, ego.a, ego.steer_angle])
+        out[f"states_{i}"] = np.array(rows)
+    np.savez_compressed(os.path.join(HERE, "prep_update_ego.npz"), **out)
+    print("update_ego:", len(ps.ego_cases()), "cases")
+
+
 def main():
     shift_interp_golden()
+    update_ego_golden()
     vel = reference_function(os.path.join(REF, "planning", "utils.py"), "rampify_profile")
     lat = reference_function(os.path.join(REF, "planning", "path_vel_decomp", "path_optim.py"), "rampify_profile")
 

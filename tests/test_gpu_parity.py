@@ -126,12 +126,13 @@ def test_negative_interpolation_argument_wraps_to_last_sample(solver_libs, oracl
     assert np.array_equal(vals[2], vals[3]) and np.array_equal(vals[3], vals[4])
 
 
-def test_sticky_regularisation_and_rollout_only(solver_libs, oracle_libs):
+@pytest.mark.parametrize("rounds", [0, 2])
+def test_sticky_regularisation_and_rollout_only(rounds, solver_libs, oracle_libs):
     """mu / mu_step survive update() calls (SURVEY.md finding 8); max_iterations = 0
     is a rollout only."""
     from tpl_b200 import scenarios as sc
     pb = sc.lateral(batch=2, horizon=200, max_iterations=8, forced=True, seed0=2)
-    q = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
+    q = sc.apply_to_batched(_factory(solver_libs, pb, rounds)(), pb)
     o = sc.apply_to_single(oracle_libs.OracleOptim(pb.model), pb, 0)
     for max_it in (8, 0, 1):
         q.max_iterations = max_it; q.update()
@@ -142,11 +143,12 @@ def test_sticky_regularisation_and_rollout_only(solver_libs, oracle_libs):
         assert int(q.termination_condition[0]) == int(o.termination_condition)
 
 
-def test_gradient_only_mode(solver_libs, oracle_libs):
+@pytest.mark.parametrize("rounds", [0, 2])
+def test_gradient_only_mode(rounds, solver_libs, oracle_libs):
     """use_quadratic_terms = False runs the reference's `ilr` (optim.c:1010-1089)."""
     from tpl_b200 import scenarios as sc
     pb = sc.smoother(batch=3, horizon=60, max_iterations=6, forced=True, seed0=9)
-    q = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
+    q = sc.apply_to_batched(_factory(solver_libs, pb, rounds)(), pb)
     q.use_quadratic_terms = False
     q.update()
     for i in range(pb.batch):
@@ -371,7 +373,8 @@ def test_user_defined_problem_through_genopt_build(tmp_path, oracle_libs):
         assert abs(float(q.traj_costs[i]) - o.traj_costs) <= common.RTOL * abs(o.traj_costs)
 
 
-def test_fp32_mode_against_fp64_oracle(solver_libs, oracle_libs):
+@pytest.mark.parametrize("rounds", [0, 2])
+def test_fp32_mode_against_fp64_oracle(rounds, solver_libs, oracle_libs):
     """Optional fp32 compute mode (BASELINE.json configs[4]): kernels compute in single
     precision, storage / cost sums / accept and stop decisions stay fp64.  Stated tolerance
     5e-4 relative on states, controls and cost against the fp64 CPU oracle after 6 forced
@@ -381,7 +384,7 @@ def test_fp32_mode_against_fp64_oracle(solver_libs, oracle_libs):
     from tpl_b200 import scenarios as sc
     pb = sc.mpc_time(batch=256, horizon=40, max_iterations=6, forced=True, seed0=4000)
     pb.scalars["ref_t_offset"][:] = 0.18
-    q = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
+    q = sc.apply_to_batched(_factory(solver_libs, pb, rounds)(), pb)
     q.precision = "fp32"
     q.update()
     worst = 0.0
@@ -397,7 +400,7 @@ def test_fp32_mode_against_fp64_oracle(solver_libs, oracle_libs):
 
     # default mode: relative-change stop; iteration counts and flags versus the oracle
     pb = sc.mpc_time(batch=128, horizon=40, max_iterations=20, forced=False, seed0=5000)
-    q = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
+    q = sc.apply_to_batched(_factory(solver_libs, pb, rounds)(), pb)
     q.precision = "fp32"
     q.update()
     same = 0

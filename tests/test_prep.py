@@ -192,3 +192,45 @@ def test_solver_warm_start_resampling(prep_lib, solver_libs):
     opt.update()
     torch.cuda.synchronize()
     assert bool(torch.isfinite(opt.traj_costs).all())
+
+
+def _run_ego_oracle(c):
+    e = oprep.EgoOracle(**c["params"], **c["init"])
+    rows = []
+    for k in range(len(c["control_acc"])):
+        e.control_acc, e.control_steer = c["control_acc"][k], c["control_steer"][k]
+        e.update(k * c["dt"], c["dt"])
+        rows.append([e.x, e.y, e.yaw, e.v, e.a, e.steer_angle])
+    return np.array(rows)
+
+
+def test_update_ego_oracle_matches_reference_golden():
+    """Golden file: the reference's SimCore.update_ego stepped through command sequences with
+    actuator dead times (incl. 0.18 s at dt = 0.01 s, where Python's `//` gives 17, not 18)."""
+    g = np.load(os.path.join(GOLDEN, "prep_update_ego.npz"))
+    for i, c in enumerate(ps.ego_cases()):
+        np.testing.assert_allclose(_run_ego_oracle(c), g[f"states_{i}"], rtol=RTOL, atol=1e-11)
+
+
+@pytest.mark.gpu
+def test_update_ego_matches_golden(prep_lib):
+    from tpl_b200.sim import BatchedEgo
+    g = np.load(os.path.join(GOLDEN, "prep_update_ego.npz"))
+    cases = ps.ego_cases()
+    for i, c in enumerate(cases):
+        # the case itself in slot 0, perturbed copies around it (they must not interfere)
+        B = 5
+        ego = BatchedEgo(B, **c["params"])
+        for n, v in c["init"].items():
+            setattr(ego, n, np.full(B, v) + np.arange(B) * (0.1 if n in ("x", "v") else 0.0))
+        rows = []
+        for k in range(len(c["control_acc"])):
+            ego.control_acc = np.full(B, c["control_acc"][k])
+            ego.control_steer = np.full(B, c["control_steer"][k]) * np.linspace(1.0, 0.5, B)
+            ego.update(k * c["dt"], c["dt"])
+            rows.append(torch.stack([getattr(ego, n)[0] for n in ("x", "y", "yaw", "v", "a", "steer_angle")]))
+        got = torch.stack(rows).cpu().numpy()
+        np.testing.assert_allclose(got, g[f"states_{i}"], rtol=RTOL, atol=1e-10)
+    from tpl_b200 import prep as P
+    with pytest.raises(P.PrepError):
+        BatchedEgo(2, capacity=4, acc_dead_time=0.18).update(0.0, 0.01)

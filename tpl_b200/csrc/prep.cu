@@ -1,6 +1,7 @@
 // Batched profile shaping in front of the lateral / velocity solves (include/tplb200_prep.h).
 // One thread = one problem (both routines are scans over the samples with a carried state);
 // arrays are [sample][problem], so every access of a warp is one 256-byte row.
+#include <cmath>
 #include <cstdio>
 #include <cuda_runtime.h>
 
@@ -153,6 +154,87 @@ __global__ void shift_interp_kernel(int B, int n, int rows, double step, const d
     }
 }
 
+// Python's float `//` (CPython float_divmod): not floor(a / b) — 0.18 // 0.01 is 17.0, not 18.0
+__host__ __device__ inline double py_floordiv(double a, double b) {
+    double mod = fmod(a, b);
+    double div = (a - mod) / b;
+    if (mod != 0.0 && ((b < 0.0) != (mod < 0.0))) div -= 1.0;
+    if (div == 0.0) return copysign(0.0, a / b);
+    double fl = floor(div);
+    if (div - fl > 0.5) fl += 1.0;
+    return fl;
+}
+
+// util.py:92-100 with Python's floored float modulo
+__device__ __forceinline__ double py_mod(double a, double m) {
+    double r = fmod(a, m);
+    if (r != 0.0 && ((r < 0.0) != (m < 0.0))) r += m;
+    return r;
+}
+
+__device__ __forceinline__ double normalize_angle(double a) {
+    const double two_pi = 3.141592653589793 * 2;
+    a = py_mod(a, two_pi);
+    a = py_mod(a + two_pi, two_pi);
+    if (a > 3.141592653589793) a -= two_pi;
+    return a;
+}
+
+// one actuator: append the command, drop what is older than the buffer may hold, pick the
+// command to apply (core.py:95-120).  History rows are [slot][B].
+__device__ __forceinline__ void dead_time_channel(double* ts, double* vals, int32_t* len_p, int B, int b, int capacity,
+                                                  double t, double dt, double command, double dead_time,
+                                                  double* applied) {
+    int len = len_p[b];
+    if (dt > 0.0) {
+        if (len < capacity) {
+            ts[(size_t)len * B + b] = t;
+            vals[(size_t)len * B + b] = command;
+            ++len;
+        }
+        const double keep = py_floordiv(dead_time, dt) + 1;   // core.py:99: dead_time // dt + 1
+        while ((double)len > keep) {                          // list.pop(0)
+            for (int i = 1; i < len; ++i) {
+                ts[(size_t)(i - 1) * B + b] = ts[(size_t)i * B + b];
+                vals[(size_t)(i - 1) * B + b] = vals[(size_t)i * B + b];
+            }
+            --len;
+        }
+        len_p[b] = len;
+    }
+    if (dead_time == 0.0 && len > 0) {
+        *applied = vals[(size_t)(len - 1) * B + b];
+        return;
+    }
+    for (int i = 0; i < len; ++i)
+        if (t - ts[(size_t)i * B + b] <= dead_time) {
+            *applied = vals[(size_t)i * B + b];
+            return;
+        }
+}
+
+__global__ void update_ego_kernel(const __grid_constant__ tplb_ego e, double t, double dt) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int B = e.batch;
+    if (b >= B) return;
+    double a = e.a[b], steer = e.steer_angle[b];
+    dead_time_channel(e.acc_t, e.acc_value, e.acc_len, B, b, e.capacity, t, dt, e.control_acc[b], e.acc_dead_time, &a);
+    dead_time_channel(e.steer_t, e.steer_value, e.steer_len, B, b, e.capacity, t, dt, e.control_steer[b],
+                      e.steer_dead_time, &steer);
+    double v = e.v[b], yaw = e.yaw[b];
+    // core.py:122-134, the reference's association; the products are not fused into the sums
+    e.x[b] = __dadd_rn(e.x[b], __dmul_rn(__dmul_rn(dt, v), cos(yaw)));
+    e.y[b] = __dadd_rn(e.y[b], __dmul_rn(__dmul_rn(dt, v), sin(yaw)));
+    const double q = v / e.v_ch;
+    const double denom = __dmul_rn(e.wheel_base, __dadd_rn(1.0, __dmul_rn(q, q)));
+    yaw = __dadd_rn(yaw, __dmul_rn(__dmul_rn(dt, v) / denom, tan(steer)));
+    e.yaw[b] = normalize_angle(yaw);
+    v = __dadd_rn(v, __dmul_rn(dt, a));
+    e.v[b] = fmin(e.max_v, fmax(e.min_v, v));
+    e.a[b] = a;
+    e.steer_angle[b] = fmin(e.max_steer_angle, fmax(-e.max_steer_angle, steer));
+}
+
 }  // namespace
 
 extern "C" {
@@ -197,6 +279,23 @@ int32_t tplb_shift_interp(int32_t batch, int32_t n, int32_t rows, double step, c
     shift_interp_kernel<<<dim3((batch + block - 1) / block, n), block, 0, static_cast<cudaStream_t>(stream)>>>(
         batch, n, rows, step, offset, kind, in, out);
     return check_launch("tplb_shift_interp");
+}
+
+int32_t tplb_update_ego(const tplb_ego* ego, double t, double dt, void* stream) {
+    if (!ego) return fail(TPLB_PREP_E_ARG, "ego is NULL");
+    if (ego->struct_bytes != (int32_t)sizeof(tplb_ego)) return fail(TPLB_PREP_E_ARG, "tplb_ego size mismatch");
+    if (ego->batch <= 0 || ego->capacity <= 0) return fail(TPLB_PREP_E_ARG, "batch and capacity must be positive");
+    if (dt > 0.0) {
+        const double need = fmax(py_floordiv(ego->acc_dead_time, dt), py_floordiv(ego->steer_dead_time, dt)) + 2;
+        if ((double)ego->capacity < need) return fail(TPLB_PREP_E_ARG, "history capacity too small for dead_time / dt");
+    }
+    if (!ego->x || !ego->y || !ego->yaw || !ego->v || !ego->a || !ego->steer_angle || !ego->control_acc ||
+        !ego->control_steer || !ego->acc_t || !ego->acc_value || !ego->acc_len || !ego->steer_t ||
+        !ego->steer_value || !ego->steer_len)
+        return fail(TPLB_PREP_E_ARG, "NULL array");
+    const int block = 128;
+    update_ego_kernel<<<(ego->batch + block - 1) / block, block, 0, static_cast<cudaStream_t>(stream)>>>(*ego, t, dt);
+    return check_launch("tplb_update_ego");
 }
 
 }  // extern "C"

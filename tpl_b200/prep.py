@@ -27,7 +27,7 @@ import torch
 
 _D = C.c_void_p
 EXPORTS = ("tplb_prep_abi_version", "tplb_prep_last_error", "tplb_rampify_velocity", "tplb_rampify_lateral",
-           "tplb_shift_interp")
+           "tplb_shift_interp", "tplb_update_ego")
 KINDS = {"linear": 0, "zero": 1}
 ABI_VERSION = 1
 

@@ -87,3 +87,25 @@ def shift_cases():
         arr = np.cumsum(rng.normal(0.0, 1.0, (n, rows)), axis=0) + rng.uniform(-5, 5)
         cases.append(dict(arr=arr, step=step, arc_len=arc))
     return cases
+
+
+EGO_DEFAULTS = dict(wheel_base=2.9, v_ch=30.0, max_v=20.0, min_v=0.0, max_steer_angle=0.6)
+
+
+def ego_case(seed, steps=300, dt=0.01, acc_dead_time=0.18, steer_dead_time=0.12, **over):
+    """A driven vehicle: initial state, parameters and the command sequence of a closed-loop run
+    (smooth steering and acceleration commands with a few steps; saturating in places)."""
+    rng = np.random.default_rng(seed)
+    p = dict(EGO_DEFAULTS, acc_dead_time=acc_dead_time, steer_dead_time=steer_dead_time, **over)
+    t = np.arange(steps) * dt
+    acc = 1.5 * np.sin(t * rng.uniform(0.5, 3.0) + rng.uniform(0, 6)) + np.where(t > rng.uniform(0.5, 2.5), -2.0, 0.5)
+    steer = 0.5 * np.sin(t * rng.uniform(0.5, 4.0) + rng.uniform(0, 6)) + rng.uniform(-0.3, 0.3)
+    init = dict(x=rng.uniform(-5, 5), y=rng.uniform(-5, 5), yaw=rng.uniform(-3.5, 3.5), v=rng.uniform(0.0, 15.0),
+                a=0.0, steer_angle=0.0)
+    return dict(params=p, init=init, dt=dt, control_acc=acc, control_steer=steer)
+
+
+def ego_cases():
+    return [ego_case(600), ego_case(601, dt=0.02), ego_case(602, acc_dead_time=0.0, steer_dead_time=0.0),
+            ego_case(603, acc_dead_time=0.05, steer_dead_time=0.3, dt=0.01), ego_case(604, steps=150, dt=0.05),
+            ego_case(605, v_ch=12.0, max_v=8.0)]
