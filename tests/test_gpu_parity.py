@@ -376,7 +376,8 @@ def test_user_defined_problem_through_genopt_build(tmp_path, oracle_libs):
 @pytest.mark.parametrize("rounds", [0, 2])
 def test_fp32_mode_against_fp64_oracle(rounds, solver_libs, oracle_libs):
     """Optional fp32 compute mode (BASELINE.json configs[4]): kernels compute in single
-    precision, storage / cost sums / accept and stop decisions stay fp64.  Stated tolerance
+    precision and keep derivative records and candidates in fp32; x, u, gains, cost sums and the
+    accept / stop decisions stay fp64.  Stated tolerance
     5e-4 relative on states, controls and cost against the fp64 CPU oracle after 6 forced
     iterations (measured 1.5e-4 on B200; BASELINE.json suggests 1e-4, which single-precision
     Riccati sweeps with 1e4 penalty weights do not reach), for locally centred coordinates;

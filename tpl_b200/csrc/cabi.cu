@@ -224,6 +224,7 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
     const size_t cx_stride = (size_t)(q.t_max + 1) * Model::X * B;
     const size_t cu_stride = (size_t)q.t_max * Model::U * B;
     constexpr int R1 = tplb::kRound1, R2 = tplb::kAlphas - tplb::kRound1;
+    using SC = tplb::scratch_t<R>;                         // storage of records and candidates
     const bool split_rollouts = two_round_rollouts(q);
     // Accepting the step inside the next linearize saves a launch and a pass over x, u while
     // launches are latency-bound; with the GPU full the separate copy kernel (high occupancy,
@@ -239,7 +240,8 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
 
     prof.before();
     launch_rollout<R, true>(q, ws, st, 0, 1, nullptr);
-    tplb::stage_cost_kernel<Model, R><<<dim3(sgx, T + 1, 1), sb, 0, st>>>(q, ws, q.x, q.u, 0, 0, 0, 0, nullptr);
+    tplb::stage_cost_kernel<Model, R, double><<<dim3(sgx, T + 1, 1), sb, 0, st>>>(
+        q, ws, (const double*)q.x, (const double*)q.u, 0, 0, 0, 0, nullptr);
     tplb::init_cost_kernel<<<sgx, sb, 0, st>>>(q, ws);
     prof.after(TPLB_K_ROLLOUT_INIT);
 
@@ -294,8 +296,9 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
                     prof.after(TPLB_K_ROLLOUT);
                 }
                 prof.before();
-                tplb::stage_cost_kernel<Model, R><<<dim3(sgx < 8 ? sgx : 8, T + 1, R2), sb, 0, st>>>(
-                    q, ws, ws.cand_x, ws.cand_u, cx_stride, cu_stride, 1, R1, ws.pending);
+                tplb::stage_cost_kernel<Model, R, SC><<<dim3(sgx < 8 ? sgx : 8, T + 1, R2), sb, 0, st>>>(
+                    q, ws, (const SC*)tplb::scratch<SC>(ws.cand_x), (const SC*)tplb::scratch<SC>(ws.cand_u), cx_stride,
+                    cu_stride, 1, R1, ws.pending);
                 prof.after(TPLB_K_STAGE_COST);
                 prof.before();
                 tplb::select_kernel<PB, 2><<<(B + PB - 1) / PB, dim3(PB, R2), 0, st>>>(q, ws);
@@ -303,13 +306,13 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
             }
             if (!fold_accept && s + 1 < q.max_iterations) {
                 prof.before();
-                tplb::accept_kernel<Model><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
+                tplb::accept_kernel<Model, SC><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
                 prof.after(TPLB_K_ACCEPT);
             }
         }
         if (q.max_iterations > 0) {
             prof.before();
-            tplb::accept_kernel<Model><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
+            tplb::accept_kernel<Model, SC><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
             prof.after(TPLB_K_ACCEPT);
         }
     }

@@ -38,6 +38,7 @@
 #pragma once
 
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "../../include/tplb200.h"
@@ -53,6 +54,15 @@ __device__ __forceinline__ int problem_of(const int32_t* list, const int32_t* co
     if (!list) return idx < B ? idx : -1;
     return idx < *count ? list[idx] : -1;
 }
+
+// Scratch that never leaves the solver — derivative records and line-search candidates, the two
+// widest streams of an iteration — is stored in the compute type: fp64, or fp32 in TPLB_FP32 mode
+// (the buffers keep their fp64 size; fp32 uses the first half).  x, u, k, K, multipliers, cost
+// terms and sums are fp64 in both modes.
+template <typename R> struct Scratch { using type = double; };
+template <> struct Scratch<float> { using type = float; };
+template <typename R> using scratch_t = typename Scratch<R>::type;
+template <typename S> __host__ __device__ __forceinline__ S* scratch(double* p) { return reinterpret_cast<S*>(p); }
 
 template <typename M>
 struct Dims {
@@ -87,6 +97,7 @@ struct Workspace {
                            //        linearisations, backward sweeps, sequential rollouts
     int32_t* pending;      // [B]  problems whose round-1 step sizes all failed (unordered list)
     int32_t* pending_count;// [1]
+    int32_t* records_f32;  // [1]  1: the derivative records were written as fp32
 };
 
 __host__ __device__ inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
@@ -109,6 +120,7 @@ __host__ __device__ inline Workspace carve(void* base, int B, int S, int t_max, 
     w.counters = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)3 * B));
     w.pending = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)B));
     w.pending_count = reinterpret_cast<int32_t*>(take(sizeof(int32_t)));
+    w.records_f32 = reinterpret_cast<int32_t*>(take(sizeof(int32_t)));
     if (total) *total = off;
     return w;
 }
@@ -291,8 +303,10 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
     for (int i = 0; i < ai; ++i) tens *= 10.0;
     const R alpha = R(1.0 / tens);
 
-    double* cx = kInit ? q.x + b : ws.cand_x + (size_t)ai * (q.t_max + 1) * X * B + b;
-    double* cu = kInit ? nullptr : ws.cand_u + (size_t)ai * q.t_max * U * B + b;
+    using XS = std::conditional_t<kInit, double, scratch_t<R>>;   // the initial rollout writes q.x itself
+    XS* cx = kInit ? reinterpret_cast<XS*>(q.x) + b
+                   : scratch<XS>(ws.cand_x) + (size_t)ai * (q.t_max + 1) * X * B + b;
+    XS* cu = kInit ? nullptr : scratch<XS>(ws.cand_u) + (size_t)ai * q.t_max * U * B + b;
     const int iB = B;                                        // component stride inside a stage
 
     auto slot = [&](int buf, int item) { return stage_in + ((size_t)buf * RI::COUNT + item) * pbn + px; };
@@ -308,7 +322,7 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
 #pragma unroll
         for (int i = 0; i < X; ++i) {
             xn[i] = R(q.x[(size_t)i * B + b]);
-            if (!kInit) __stcs(cx + (size_t)i * B, (double)xn[i]);
+            if (!kInit) __stcs(cx + (size_t)i * B, (XS)xn[i]);
         }
     }
     double total = 0.0;
@@ -351,9 +365,9 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
 #pragma unroll
             for (int j = 0; j < NSC; ++j) sc[j] = R(*slot(buf, RI::O_SC + j));
             if (!kInit) {
-                double* cut = cu + (size_t)t * U * B;
+                XS* cut = cu + (size_t)t * U * B;
 #pragma unroll
-                for (int d = 0; d < U; ++d) __stcs(cut + d * iB, (double)un[d]);   // streaming: keep K, k, x, u in L2
+                for (int d = 0; d < U; ++d) __stcs(cut + d * iB, (XS)un[d]);       // streaming: keep K, k, x, u in L2
             }
             if (kCost) {
                 R lam[D::Cs], c;
@@ -363,12 +377,12 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
                 total += (double)c;
             }
             step_state<M, kScheme>(P, xn, un, sc, R(t), R(q.dt), xnext);
-            double* cxt = cx + (size_t)(t + 1) * X * B;
+            XS* cxt = cx + (size_t)(t + 1) * X * B;
 #pragma unroll
             for (int i = 0; i < X; ++i) {
                 xn[i] = xnext[i];
-                if (kInit) cxt[i * iB] = xnext[i];
-                else __stcs(cxt + i * iB, (double)xnext[i]);
+                if (kInit) cxt[i * iB] = (XS)xnext[i];
+                else __stcs(cxt + i * iB, (XS)xnext[i]);
             }
         }
         buf = nxt;
@@ -398,9 +412,10 @@ rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int a_begin, 
 // xs + a*x_stride, us + a*u_stride (the initial rollout passes q.x / q.u, 1 candidate).
 // `list` != NULL: work items are entries of the pending list (round 2 of the line search).
 // ---------------------------------------------------------------------------------
-template <typename M, typename R>
+// S: element type of xs / us (double for q.x / q.u, scratch_t<R> for the candidates).
+template <typename M, typename R, typename S>
 __device__ __forceinline__ void dev_stage_cost(const tplb_batch& q, const Workspace& ws,
-                                               const double* xs, const double* us, size_t x_stride,
+                                               const S* xs, const S* us, size_t x_stride,
                                                size_t u_stride, int check_running, int b, int t, int a) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U, C = D::C;
@@ -409,8 +424,8 @@ __device__ __forceinline__ void dev_stage_cost(const tplb_batch& q, const Worksp
     const int T = q.horizon;
     const int scene = __ldg(q.scene_index + b);
     const ParamView<R> P = param_view_scene<R>(q, scene);
-    const double* xa = xs + a * x_stride + b;
-    const double* ua = us + a * u_stride + b;
+    const S* xa = xs + a * x_stride + b;
+    const S* ua = us + a * u_stride + b;
 
     R x[X], sc[D::NSCs], c;
 #pragma unroll
@@ -434,14 +449,14 @@ __device__ __forceinline__ void dev_stage_cost(const tplb_batch& q, const Worksp
 
 // One thread = one (problem, stage, candidate).  With a pending list the x-blocks stride over
 // the list, so the grid can stay small when few problems are pending.
-template <typename M, typename R>
+template <typename M, typename R, typename S>
 __global__ void stage_cost_kernel(const __grid_constant__ tplb_batch q, Workspace ws,
-                                  const double* xs, const double* us, size_t x_stride, size_t u_stride,
+                                  const S* xs, const S* us, size_t x_stride, size_t u_stride,
                                   int check_running, int a_begin, const int32_t* list) {
     const int n = list ? *ws.pending_count : q.batch;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int b = list ? list[i] : i;
-        dev_stage_cost<M, R>(q, ws, xs, us, x_stride, u_stride, check_running, b, blockIdx.y, a_begin + blockIdx.z);
+        dev_stage_cost<M, R, S>(q, ws, xs, us, x_stride, u_stride, check_running, b, blockIdx.y, a_begin + blockIdx.z);
     }
 }
 
@@ -456,6 +471,8 @@ __global__ void stage_cost_round1_kernel(const __grid_constant__ tplb_batch q, W
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B || !ws.running[b]) return;
     const size_t x_stride = (size_t)(q.t_max + 1) * X * B, u_stride = (size_t)q.t_max * U * B;
+    const scratch_t<R>* cand_x = scratch<scratch_t<R>>(ws.cand_x);
+    const scratch_t<R>* cand_u = scratch<scratch_t<R>>(ws.cand_u);
     const int scene = __ldg(q.scene_index + b);
     const ParamView<R> P = param_view_scene<R>(q, scene);
     R sc[D::NSCs], x[kRound1][X], c[kRound1];
@@ -463,13 +480,13 @@ __global__ void stage_cost_round1_kernel(const __grid_constant__ tplb_batch q, W
 #pragma unroll
     for (int a = 0; a < kRound1; ++a)
 #pragma unroll
-        for (int i = 0; i < X; ++i) x[a][i] = R(ws.cand_x[a * x_stride + ((size_t)t * X + i) * B + b]);
+        for (int i = 0; i < X; ++i) x[a][i] = R(cand_x[a * x_stride + ((size_t)t * X + i) * B + b]);
     if (t < T) {
         R u[kRound1][U], lam[D::Cs], w[D::Cs];
 #pragma unroll
         for (int a = 0; a < kRound1; ++a)
 #pragma unroll
-            for (int i = 0; i < U; ++i) u[a][i] = R(ws.cand_u[a * u_stride + ((size_t)t * U + i) * B + b]);
+            for (int i = 0; i < U; ++i) u[a][i] = R(cand_u[a * u_stride + ((size_t)t * U + i) * B + b]);
 #pragma unroll
         for (int cc = 0; cc < C; ++cc) {
             lam[cc] = R(q.lagrange_multiplier[((size_t)t * C + cc) * B + b]);
@@ -567,12 +584,12 @@ __device__ __forceinline__ void dev_linearize(const tplb_batch& q, const Workspa
         // the step accepted by the previous line search becomes the trajectory (optim.c:844-848)
         const int win = ws.winner[b];
         if (win >= 0) {
-            const double* cx = ws.cand_x + (size_t)win * (q.t_max + 1) * X * B + b;
-            const double* cu = ws.cand_u + (size_t)win * q.t_max * U * B + b;
+            const scratch_t<R>* cx = scratch<scratch_t<R>>(ws.cand_x) + (size_t)win * (q.t_max + 1) * X * B + b;
+            const scratch_t<R>* cu = scratch<scratch_t<R>>(ws.cand_u) + (size_t)win * q.t_max * U * B + b;
 #pragma unroll
             for (int i = 0; i < X; ++i) {
                 const size_t idx = ((size_t)t * X + i) * B + b;
-                const double xv = cx[((size_t)t * X + i) * B];
+                const double xv = (double)cx[((size_t)t * X + i) * B];
                 x[i] = R(xv);
                 if (q.keep_previous) q.prev_x[idx] = q.x[idx];
                 q.x[idx] = xv;
@@ -581,7 +598,7 @@ __device__ __forceinline__ void dev_linearize(const tplb_batch& q, const Workspa
 #pragma unroll
                 for (int d = 0; d < U; ++d) {
                     const size_t idx = ((size_t)t * U + d) * B + b;
-                    const double uv = cu[((size_t)t * U + d) * B];
+                    const double uv = (double)cu[((size_t)t * U + d) * B];
                     u[d] = R(uv);
                     if (q.keep_previous) q.prev_k[idx] = q.k[idx];
                     q.u[idx] = uv;
@@ -619,10 +636,11 @@ __device__ __forceinline__ void dev_linearize(const tplb_batch& q, const Workspa
         M::dynamics_jacobians(P, x, u, sc, R(t), R(q.dt), blk + D::OFF_FX, blk + D::OFF_FU);
         M::cost_gradients(P, x, u, lam, w, sc, R(t), R(q.dt), blk + D::OFF_LX, blk + D::OFF_LU);
     }
-    double* out = ws.deriv + (size_t)t * D::COMPACT * B + b;
+    scratch_t<R>* out = scratch<scratch_t<R>>(ws.deriv) + (size_t)t * D::COMPACT * B + b;
 #pragma unroll
     for (int e = 0; e < D::DENSE; ++e)
         if (M::deriv_owner(e)) out[(size_t)M::deriv_slot(e) * B] = blk[e];
+    if (b == 0 && t == 0) *ws.records_f32 = sizeof(scratch_t<R>) == sizeof(float);
 }
 
 template <typename M, typename R, bool kForce, bool kAccept>
@@ -641,12 +659,14 @@ __global__ void expand_derivatives_kernel(const __grid_constant__ tplb_batch q, 
     const int t = blockIdx.y;
     const int B = q.batch;
     if (b >= B) return;
+    const bool f32 = *ws.records_f32 != 0;                   // format the last linearisation wrote
     const double* in = ws.deriv + (size_t)t * D::COMPACT * B + b;
+    const float* in32 = scratch<float>(ws.deriv) + (size_t)t * D::COMPACT * B + b;
     double* out = dense + (size_t)t * D::DENSE * B + b;
 #pragma unroll
     for (int e = 0; e < D::DENSE; ++e) {
         const int s = M::deriv_slot(e);
-        out[(size_t)e * B] = s >= 0 ? in[(size_t)s * B] : (s == -2 ? 1.0 : 0.0);
+        out[(size_t)e * B] = s >= 0 ? (f32 ? (double)in32[(size_t)s * B] : in[(size_t)s * B]) : (s == -2 ? 1.0 : 0.0);
     }
 }
 
@@ -728,7 +748,7 @@ __device__ __forceinline__ void dev_backward(const tplb_batch& q, const Workspac
 
     R rec[NC], nxt[NC], ub[U], hib[U], lob[U], nub[U], nhib[U], nlob[U];
     auto fetch = [&](int t, R* r, R* uu, R* hh, R* ll) {
-        const double* blk = ws.deriv + (size_t)t * NC * B + b;
+        const scratch_t<R>* blk = scratch<scratch_t<R>>(ws.deriv) + (size_t)t * NC * B + b;
 #pragma unroll
         for (int s = 0; s < M::DERIV_COMPACT; ++s) r[s] = R(__ldcs(blk + (size_t)s * B));   // read once
 #pragma unroll
@@ -931,7 +951,7 @@ __device__ __forceinline__ void dev_backward_first_order(const tplb_batch& q, co
         M::end_derivatives(P, xT, sc, R(T), R(q.dt), Vx, Vxx);
     }
     for (int t = T - 1; t >= 0; --t) {
-        const double* blk = ws.deriv + (size_t)t * D::COMPACT * B + b;
+        const scratch_t<R>* blk = scratch<scratch_t<R>>(ws.deriv) + (size_t)t * D::COMPACT * B + b;
         auto val = [&](int e) {
             const int s = M::deriv_slot(e);
             return s >= 0 ? R(blk[(size_t)s * B]) : (s == -2 ? R(1) : R(0));
@@ -1081,36 +1101,37 @@ select_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
 }
 
 // copy the accepted candidate into x, u (and keep prev_x, prev_k) — thread per (problem, stage)
-template <typename M>
+// S: element type of the candidates (scratch_t of the precision that rolled them out)
+template <typename M, typename S>
 __device__ __forceinline__ void dev_accept(const tplb_batch& q, const Workspace& ws, int b, int t) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U;
     const int B = q.batch;
     const int win = ws.winner[b];
     if (win < 0) return;
-    const double* cx = ws.cand_x + (size_t)win * (q.t_max + 1) * X * B + b;
-    const double* cu = ws.cand_u + (size_t)win * q.t_max * U * B + b;
+    const S* cx = scratch<S>(ws.cand_x) + (size_t)win * (q.t_max + 1) * X * B + b;
+    const S* cu = scratch<S>(ws.cand_u) + (size_t)win * q.t_max * U * B + b;
 #pragma unroll
     for (int i = 0; i < X; ++i) {
         const size_t idx = ((size_t)t * X + i) * B + b;
         if (q.keep_previous) q.prev_x[idx] = q.x[idx];
-        q.x[idx] = cx[((size_t)t * X + i) * B];
+        q.x[idx] = (double)cx[((size_t)t * X + i) * B];
     }
     if (t < q.horizon) {
 #pragma unroll
         for (int d = 0; d < U; ++d) {
             const size_t idx = ((size_t)t * U + d) * B + b;
             if (q.keep_previous) q.prev_k[idx] = q.k[idx];
-            q.u[idx] = cu[((size_t)t * U + d) * B];
+            q.u[idx] = (double)cu[((size_t)t * U + d) * B];
         }
     }
 }
 
-template <typename M>
+template <typename M, typename S>
 __global__ void accept_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= q.batch) return;
-    dev_accept<M>(q, ws, b, blockIdx.y);                     // rows 0..T
+    dev_accept<M, S>(q, ws, b, blockIdx.y);                  // rows 0..T
 }
 
 __device__ __forceinline__ void dev_finalize(const tplb_batch& q, int b, int lg_done) {
