@@ -234,3 +234,75 @@ def test_update_ego_matches_golden(prep_lib):
     from tpl_b200 import prep as P
     with pytest.raises(P.PrepError):
         BatchedEgo(2, capacity=4, acc_dead_time=0.18).update(0.0, 0.01)
+
+
+@pytest.mark.gpu
+def test_batched_closed_loop_against_the_oracle_loop(prep_lib, solver_libs, oracle_libs):
+    """Rows a (solver), a11 (shift) and f4 (vehicle step) as one closed loop on the device, as
+    model_predictive_controller_time.py:150-175 + simulation/core.py:91-134 run it per vehicle:
+    x0 from the vehicle, update(), commands = x[1][a], x[1][delta] (clamped), five 0.01 s vehicle
+    steps with actuator dead times, shift(1) as warm start of the next cycle.  Every vehicle of the
+    batch is checked against the same loop built from the CPU oracles, 1e-9 over 12 cycles (measured
+    1e-15).  Three forced iterations per cycle keep the solves off the round-off plateau: with five
+    iterations and the relative-change stop, one accept/reject decision on the plateau differs
+    (SURVEY.md finding 9) and the loops drift apart by 8e-5 — both are valid closed loops."""
+    from tpl_b200 import scenarios as sc
+    from tpl_b200.batched import BatchedOptim
+    from tpl_b200.sim import BatchedEgo
+    B, T, cycles, sub, sim_dt, cycle = 6, 40, 12, 5, 0.01, 0.05
+    pb = sc.mpc_time(batch=B, horizon=T, max_iterations=3, forced=True, seed0=2600)
+    wb, cog = 3.165, 0.5
+    veh = dict(wheel_base=wb, v_ch=32.0, max_v=30.0, min_v=0.0, max_steer_angle=0.7,
+               acc_dead_time=0.03, steer_dead_time=0.05)
+
+    def x0_of(x, y, yaw, steer, v, a):                       # controller's view of the vehicle, :150-157
+        return [x + np.cos(yaw) * cog * wb, y + np.sin(yaw) * cog * wb, yaw, steer, v, a]
+
+    # ---- device loop ----------------------------------------------------------------
+    opt = sc.apply_to_batched(BatchedOptim(solver_libs[pb.model], batch=B, scenes=pb.scenes, horizon_max=T), pb)
+    ego = BatchedEgo(B, **veh)
+    ego.x = pb.x0[:, 0] - np.cos(pb.x0[:, 2]) * cog * wb
+    ego.y = pb.x0[:, 1] - np.sin(pb.x0[:, 2]) * cog * wb
+    ego.yaw, ego.v = pb.x0[:, 2], pb.x0[:, 4]
+    t, log = 0.0, []
+    for c in range(cycles):
+        x0 = torch.stack([ego.x + torch.cos(ego.yaw) * cog * wb, ego.y + torch.sin(ego.yaw) * cog * wb,
+                          ego.yaw, ego.steer_angle, ego.v, ego.a], dim=1)
+        opt.set_initial_state(x0)
+        opt.params.ref_t_offset = t
+        opt.update()
+        ego.control_acc = opt.x[:, 1, 5].clamp(-3.0, 3.0)
+        ego.control_steer = opt.x[:, 1, 3].clamp(-0.7, 0.7)
+        for k in range(sub):
+            ego.update(t, sim_dt)
+            t += sim_dt
+        opt.shift(1)
+        log.append(torch.stack([ego.x, ego.y, ego.yaw, ego.v, ego.a, ego.steer_angle], dim=1).cpu().numpy())
+    got = np.stack(log)                                      # (cycles, B, 6)
+
+    # ---- the same loop from the CPU oracles, vehicle by vehicle ---------------------------
+    worst, per_cycle = 0.0, [0.0] * cycles
+    for i in range(B):
+        o = sc.apply_to_single(oracle_libs.OracleOptim(pb.model), pb, i)
+        e = oprep.EgoOracle(**veh, x=pb.x0[i, 0] - np.cos(pb.x0[i, 2]) * cog * wb,
+                            y=pb.x0[i, 1] - np.sin(pb.x0[i, 2]) * cog * wb, yaw=pb.x0[i, 2], v=pb.x0[i, 4],
+                            a=0.0, steer_angle=0.0)
+        t = 0.0
+        for c in range(cycles):
+            o.x[0] = x0_of(e.x, e.y, e.yaw, e.steer_angle, e.v, e.a)
+            o.params.ref_t_offset = t
+            o.update()
+            e.control_acc = min(3.0, max(-3.0, o.x[1][5]))
+            e.control_steer = min(0.7, max(-0.7, o.x[1][3]))
+            for k in range(sub):
+                e.update(t, sim_dt)
+                t += sim_dt
+            o.shift(1)
+            want = np.array([e.x, e.y, e.yaw, e.v, e.a, e.steer_angle])
+            dev = float(np.max(np.abs(got[c, i] - want) / np.maximum(1.0, np.abs(want))))
+            per_cycle[c] = max(per_cycle[c], dev)
+            worst = max(worst, dev)
+    print("closed loop, worst deviation per cycle:", " ".join(f"{d:.1e}" for d in per_cycle))
+    print(f"closed loop, {cycles} cycles: worst deviation from the oracle loop {worst:.2e}")
+    assert worst <= RTOL
+    assert np.all(got[-1, :, 3] > 1.0)                       # the vehicles are driving
