@@ -162,42 +162,34 @@ int32_t tplb_update_profiled(const tplb_batch* qp, void* stream_, float* ms_by_c
 namespace {
 
 constexpr int PB = 32;                                     // problems per rollout / select block
-// rollouts of candidates [a_begin, a_begin + a_count) for every problem (list == NULL) or
-// for the problems of the pending list
-template <typename R, bool kInit, bool kCost = false>
-void launch_rollout(const tplb_batch& q, const tplb::Workspace& ws, cudaStream_t st,
-                    int a_begin, int a_count, const int32_t* list) {
-    const dim3 grid((q.batch + PB - 1) / PB), block(PB, kInit ? 1 : a_count);
-    const bool dense = !kInit && !kCost && q.batch >= 16384;         // enough blocks to want 2 per SM
+// rollouts of candidates [a_begin, a_begin + NA) for every problem (list == NULL) or for the
+// problems of the pending list
+template <typename R, int NA, bool kInit, bool kCost = false>
+void launch_rollout(const tplb_batch& q, const tplb::Workspace& ws, cudaStream_t st, int a_begin,
+                    const int32_t* list) {
+    const dim3 grid((q.batch + PB - 1) / PB), block(PB, NA);
     const size_t smem = tplb::rollout_smem_bytes<Model, kInit, kCost>(PB);
-#define TPLB_ROLLOUT_K(SCHEME, MINB)                                                                  \
+#define TPLB_ROLLOUT(SCHEME)                                                                          \
     do {                                                                                              \
-        auto kern = tplb::rollout_kernel<Model, R, PB, kInit, SCHEME, MINB, kCost>;                           \
+        auto kern = tplb::rollout_kernel<Model, R, PB, NA, kInit, SCHEME, kCost>;                     \
         if (smem > 48 * 1024)   /* opt in per launch: the attribute belongs to the current device */ \
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
         kern<<<grid, block, smem, st>>>(q, ws, a_begin, list);                                        \
     } while (0)
-#define TPLB_ROLLOUT(SCHEME)                                          \
-    if constexpr (kCost) TPLB_ROLLOUT_K(SCHEME, 1);                   \
-    else if (dense) TPLB_ROLLOUT_K(SCHEME, (kInit ? 1 : 2));          \
-    else TPLB_ROLLOUT_K(SCHEME, 1)
     switch (q.integrator_type) {
         case TPLB_EULER: TPLB_ROLLOUT(TPLB_EULER); break;
         case TPLB_HEUN: TPLB_ROLLOUT(TPLB_HEUN); break;
         default: TPLB_ROLLOUT(TPLB_RK4); break;
     }
 #undef TPLB_ROLLOUT
-#undef TPLB_ROLLOUT_K
 }
 
-// tplb_batch.line_search_rounds.  Auto: two rounds once the batch fills the chip — the six
-// small step sizes are then rolled out only for the problems that need them; below that
-// every phase is latency-bound and rolling out all 8 at once costs nothing.
-// (TPLB_TWO_ROUND_ROLLOUTS=0/1 overrides, for experiments.)
-bool two_round_rollouts(const tplb_batch& q) {
-    if (const char* e = std::getenv("TPLB_TWO_ROUND_ROLLOUTS")) return std::atoi(e) != 0;
+// tplb_batch.line_search_rounds: 2 selects the throughput sequence, 1 the latency sequence,
+// 0 decides by batch size (measured on B200: 8192 and 12288 problems are faster with the
+// latency sequence, 16384 and more with the throughput sequence).
+bool throughput_sequence(const tplb_batch& q) {
     if (q.line_search_rounds != 0) return q.line_search_rounds == 2;
-    return q.batch >= 16384;     // measured on B200: 8192 -> one round, 16384 -> two rounds
+    return q.batch >= 16384;
 }
 
 template <typename R>
@@ -225,21 +217,22 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
     const size_t cu_stride = (size_t)q.t_max * Model::U * B;
     constexpr int R1 = tplb::kRound1, R2 = tplb::kAlphas - tplb::kRound1;
     using SC = tplb::scratch_t<R>;                         // storage of records and candidates
-    const bool split_rollouts = two_round_rollouts(q);
-    // Accepting the step inside the next linearize saves a launch and a pass over x, u while
-    // launches are latency-bound; with the GPU full the separate copy kernel (high occupancy,
-    // at the HBM roofline) plus a plain linearize is faster than the folded one.
-    bool fold_accept = !split_rollouts;
-    if (const char* e = std::getenv("TPLB_FOLD_ACCEPT")) fold_accept = std::atoi(e) != 0;
-    bool sum_in_rollout = split_rollouts;
-    if (const char* e = std::getenv("TPLB_SUM_IN_ROLLOUT")) sum_in_rollout = split_rollouts && std::atoi(e) != 0;
+    // Two launch sequences with identical results:
+    //   latency    — the batch cannot fill the GPU: fewest launches.  All 8 step sizes roll out at
+    //                once, stage costs of the candidates in stage-parallel kernels, the accepted
+    //                step is installed by the next linearize.
+    //   throughput — GPU full, every kernel streams from HBM: fewest bytes.  Two-round rollouts
+    //                that add up their own stage costs, stand-alone accept (high occupancy, at
+    //                the HBM roofline) in front of a plain linearize.
+    const bool throughput = throughput_sequence(q);
+    const bool fold_accept = !throughput;
 
     prof.before();
     tplb::stage_constants_kernel<Model><<<dim3((S + sb - 1) / sb, T + 1), sb, 0, st>>>(q, ws);
     prof.after(TPLB_K_STAGE_CONSTS);
 
     prof.before();
-    launch_rollout<R, true>(q, ws, st, 0, 1, nullptr);
+    launch_rollout<R, 1, true>(q, ws, st, 0, nullptr);
     tplb::stage_cost_kernel<Model, R, double><<<dim3(sgx, T + 1, 1), sb, 0, st>>>(
         q, ws, (const double*)q.x, (const double*)q.u, 0, 0, 0, 0, nullptr);
     tplb::init_cost_kernel<<<sgx, sb, 0, st>>>(q, ws);
@@ -262,39 +255,32 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
                 tplb::backward_first_order_kernel<Model, R><<<pgrid, pb, 0, st>>>(q, ws, s);
             prof.after(TPLB_K_BACKWARD);
 
-            if (sum_in_rollout) {
-                // GPU full: the rollouts add up their own stage costs, nothing is read twice
+            if (throughput) {
+                // round 1: alpha = 1, 0.1; round 2: the other six for the problems still pending
                 prof.before();
-                launch_rollout<R, false, true>(q, ws, st, 0, R1, nullptr);
+                launch_rollout<R, R1, false, true>(q, ws, st, 0, nullptr);
                 prof.after(TPLB_K_ROLLOUT);
                 prof.before();
                 tplb::select_kernel<PB, 1, true><<<(B + PB - 1) / PB, dim3(PB, R1), 0, st>>>(q, ws);
                 prof.after(TPLB_K_SELECT);
                 prof.before();
-                launch_rollout<R, false, true>(q, ws, st, R1, R2, ws.pending);
+                launch_rollout<R, R2, false, true>(q, ws, st, R1, ws.pending);
                 prof.after(TPLB_K_ROLLOUT);
                 prof.before();
                 tplb::select_kernel<PB, 2, true><<<(B + PB - 1) / PB, dim3(PB, R2), 0, st>>>(q, ws);
                 prof.after(TPLB_K_SELECT);
             } else {
-                // round 1: alpha = 1, 0.1
                 prof.before();
-                if (split_rollouts) launch_rollout<R, false>(q, ws, st, 0, R1, nullptr);
-                else launch_rollout<R, false>(q, ws, st, 0, tplb::kAlphas, nullptr);
+                launch_rollout<R, tplb::kAlphas, false>(q, ws, st, 0, nullptr);
                 prof.after(TPLB_K_ROLLOUT);
+                // round 1: alpha = 1, 0.1
                 prof.before();
                 tplb::stage_cost_round1_kernel<Model, R><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
                 prof.after(TPLB_K_STAGE_COST);
                 prof.before();
                 tplb::select_kernel<PB, 1><<<(B + PB - 1) / PB, dim3(PB, R1), 0, st>>>(q, ws);
                 prof.after(TPLB_K_SELECT);
-
                 // round 2: alpha = 1e-2 .. 1e-7 for the problems still pending
-                if (split_rollouts) {
-                    prof.before();
-                    launch_rollout<R, false>(q, ws, st, R1, R2, ws.pending);
-                    prof.after(TPLB_K_ROLLOUT);
-                }
                 prof.before();
                 tplb::stage_cost_kernel<Model, R, SC><<<dim3(sgx < 8 ? sgx : 8, T + 1, R2), sb, 0, st>>>(
                     q, ws, (const SC*)tplb::scratch<SC>(ws.cand_x), (const SC*)tplb::scratch<SC>(ws.cand_u), cx_stride,

@@ -220,8 +220,6 @@ __device__ __forceinline__ void step_state(const PV& P, const R* x, const R* u, 
 //   !kInit  : line search, block = PB problems x 8 step sizes; threadIdx.x = problem
 //             (coalesced), threadIdx.y = i with alpha_i = 1 / 10^i (optim.c:863);
 //             candidates go to ws.cand_x / ws.cand_u (the reference's next_x / next_u)
-//   kMinBlocks : 2 caps registers at 128 so two blocks fit per SM — more resident warps for
-//             batches that fill the chip; 1 keeps everything in registers for small batches
 // Dynamic shared memory: rollout_smem_bytes<M, kInit>(PB) (input staging, shared by a problem's candidates).
 // ---------------------------------------------------------------------------------
 // number of doubles one rollout stage reads per thread
@@ -234,56 +232,78 @@ struct RolloutInputs {
                          COUNT = O_LAM + (kCost ? M::C : 0);   // kCost: the multipliers of the stage cost
 };
 
-// where stage t of one staged item lives: base + t * stride (+ problem or scene index)
-struct StageSource {
-    const double* base;
-    size_t stride;
-};
-
 constexpr int kRolloutSlots = 3;                             // stages in flight in the staging ring
 
 template <typename M, bool kInit, bool kCost = false>
 __host__ __device__ inline size_t rollout_smem_bytes(int problems_per_block) {
     using RI = RolloutInputs<M, kInit, kCost>;
-    return sizeof(StageSource) * RI::COUNT + sizeof(double) * kRolloutSlots * RI::COUNT * problems_per_block;
+    return sizeof(double) * kRolloutSlots * RI::COUNT * problems_per_block;
 }
 
-template <typename M, bool kInit, bool kCost>
-__device__ __forceinline__ StageSource rollout_source(const tplb_batch& q, const Workspace& ws, int e) {
+// global address of staged item E at stage t for problem b (scene for the stage constants)
+template <typename M, bool kInit, bool kCost, int E>
+__device__ __forceinline__ const double* rollout_source(const tplb_batch& q, const Workspace& ws, size_t t,
+                                                        int b, int scene) {
     using RI = RolloutInputs<M, kInit, kCost>;
-    constexpr int X = M::X, U = M::U, NSC = M::NUM_STAGE_CONSTS;
+    constexpr int X = M::X, U = M::U, NSC = M::NUM_STAGE_CONSTS, C = M::C;
     const size_t B = q.batch;
-    if (e < RI::O_K) return {q.u + (e - RI::O_U) * B, U * B};
-    if (e < RI::O_HI) return {q.k + (e - RI::O_K) * B, U * B};
-    if (e < RI::O_LO) return {q.u_max + (e - RI::O_HI) * B, U * B};
-    if (e < RI::O_KK) return {q.u_min + (e - RI::O_LO) * B, U * B};
-    if (e < RI::O_X) return {q.K + (e - RI::O_KK) * B, (size_t)U * X * B};
-    if (e < RI::O_SC) return {q.x + (e - RI::O_X) * B, X * B};
-    if (e < RI::O_LAM) return {ws.stage_consts + (size_t)(e - RI::O_SC) * q.scenes, (size_t)NSC * q.scenes};
-    return {q.lagrange_multiplier + (e - RI::O_LAM) * B, (size_t)M::C * B};
+    if constexpr (E < RI::O_K) return q.u + (t * U + (E - RI::O_U)) * B + b;
+    else if constexpr (E < RI::O_HI) return q.k + (t * U + (E - RI::O_K)) * B + b;
+    else if constexpr (E < RI::O_LO) return q.u_max + (t * U + (E - RI::O_HI)) * B + b;
+    else if constexpr (E < RI::O_KK) return q.u_min + (t * U + (E - RI::O_LO)) * B + b;
+    else if constexpr (E < RI::O_X) return q.K + (t * (U * X) + (E - RI::O_KK)) * B + b;
+    else if constexpr (E < RI::O_SC) return q.x + (t * X + (E - RI::O_X)) * B + b;
+    else if constexpr (E < RI::O_LAM) return ws.stage_consts + (t * NSC + (E - RI::O_SC)) * q.scenes + scene;
+    else return q.lagrange_multiplier + (t * C + (E - RI::O_LAM)) * B + b;
 }
 
-// One thread = one (problem, step size).  All step sizes of a problem read the same inputs
-// (u, k, bounds, K, x, stage constants of stage t), so the block stages them ONCE per problem:
-// `smem` = StageSource[COUNT] followed by a ring of kRolloutSlots stages, [slot][COUNT][PB]
-// doubles.  The candidates of a problem share the copies of a stage (item e is copied by
-// candidate e mod blockDim.y), asynchronously and one stage ahead; one __syncthreads per
-// stage publishes them.  With three slots the copy of stage t+2 can never overwrite what a
-// slower warp still reads for stage t.  `live` == false: the thread only keeps the barriers.
+// copies items [E0, E1) of stage t into the ring slot `dst` (this problem's column)
+template <typename M, bool kInit, bool kCost, int PB, int E0, int E1>
+__device__ __forceinline__ void rollout_fetch_range(const tplb_batch& q, const Workspace& ws, size_t t, int b,
+                                                    int scene, double* dst) {
+    if constexpr (E0 < E1) {
+        async_copy8(dst + E0 * PB, rollout_source<M, kInit, kCost, E0>(q, ws, t, b, scene));
+        rollout_fetch_range<M, kInit, kCost, PB, E0 + 1, E1>(q, ws, t, b, scene, dst);
+    }
+}
+
+// candidate R of NA copies the R-th chunk of the items; `yy` is uniform in a warp, so the
+// chain of comparisons is a uniform jump and every warp issues only its own copies
+template <typename M, bool kInit, bool kCost, int PB, int NA, int R = 0>
+__device__ __forceinline__ void rollout_fetch(const tplb_batch& q, const Workspace& ws, size_t t, int b, int scene,
+                                              double* dst, int yy) {
+    using RI = RolloutInputs<M, kInit, kCost>;
+    constexpr int CH = (RI::COUNT + NA - 1) / NA;
+    if constexpr (R < NA) {
+        if (yy == R) {
+            constexpr int E0 = R * CH, E1 = (R + 1) * CH < RI::COUNT ? (R + 1) * CH : RI::COUNT;
+            rollout_fetch_range<M, kInit, kCost, PB, (E0 < RI::COUNT ? E0 : RI::COUNT), E1>(q, ws, t, b, scene, dst);
+        } else {
+            rollout_fetch<M, kInit, kCost, PB, NA, R + 1>(q, ws, t, b, scene, dst, yy);
+        }
+    }
+}
+
+// One thread = one (problem, step size); block = PB problems (threadIdx.x) x NA step sizes.
+// All step sizes of a problem read the same inputs (u, k, bounds, K, x, stage constants of
+// stage t), so the block stages them ONCE per problem: `smem` is a ring of kRolloutSlots
+// stages, [slot][COUNT][PB] doubles.  The candidates of a problem share the copies of a stage
+// (each a contiguous chunk of the items), asynchronously and one stage ahead; one
+// __syncthreads per stage publishes them.  With three slots the copy of stage t+2 can never
+// overwrite what a slower warp still reads for stage t.  `live` == false: the thread only
+// keeps the barriers.
 // kCost: the thread also evaluates the stage costs of its candidate and adds them up in the
 // reference's order (optim.c:773-790) -> ws.cand_cost; used when the GPU is full, where
 // re-reading the candidates in a separate cost kernel costs more than the longer chain.
-template <typename M, typename R, bool kInit, int kScheme, bool kCost>
+template <typename M, typename R, int PB, int NA, bool kInit, int kScheme, bool kCost>
 __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace& ws, int b, int ai, bool live,
                                             unsigned char* smem) {
     using D = Dims<M>;
     using RI = RolloutInputs<M, kInit, kCost>;
     constexpr int X = D::X, U = D::U, NSC = D::NSC;
     const int B = q.batch;
-    const int px = threadIdx.x, pbn = blockDim.x, yy = threadIdx.y, na = blockDim.y;
-    StageSource* src = reinterpret_cast<StageSource*>(smem);
-    double* stage_in = reinterpret_cast<double*>(smem + sizeof(StageSource) * RI::COUNT);
-    for (int e = yy * pbn + px; e < RI::COUNT; e += pbn * na) src[e] = rollout_source<M, kInit, kCost>(q, ws, e);
+    const int px = threadIdx.x, yy = threadIdx.y;
+    double* stage_in = reinterpret_cast<double*>(smem) + px;
 
     if (kInit) {
         if (live) {
@@ -309,13 +329,9 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
     XS* cu = kInit ? nullptr : scratch<XS>(ws.cand_u) + (size_t)ai * q.t_max * U * B + b;
     const int iB = B;                                        // component stride inside a stage
 
-    auto slot = [&](int buf, int item) { return stage_in + ((size_t)buf * RI::COUNT + item) * pbn + px; };
-    auto fetch = [&](int t, int buf) {
-        for (int e = yy; e < RI::COUNT; e += na) {
-            const StageSource s = src[e];
-            async_copy8(slot(buf, e), s.base + (size_t)t * s.stride + ((e >= RI::O_SC && e < RI::O_LAM) ? scene : b));
-        }
-    };
+    // ring slot `buf` of this problem: item e at ring(buf)[e * PB]
+    auto ring = [&](int buf) { return stage_in + buf * (RI::COUNT * PB); };
+    auto fetch = [&](int t, int buf) { rollout_fetch<M, kInit, kCost, PB, NA>(q, ws, (size_t)t, b, scene, ring(buf), yy); };
 
     R xn[X];
     if (live) {
@@ -332,7 +348,6 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
         for (int cc = 0; cc < D::C; ++cc) weight[cc] = R(q.barrier_weight[(size_t)cc * B + b]);
     }
 
-    __syncthreads();                                         // source table written
     if (live) fetch(0, 0);
     async_commit();
     int buf = 0;
@@ -344,26 +359,27 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
         __syncthreads();                                     // ... and everybody else's
 
         if (live) {
+            const double* in = ring(buf);                    // stage t of this problem, item e at in[e * PB]
             R un[U], xnext[X], sc[D::NSCs];
 #pragma unroll
             for (int d = 0; d < U; ++d) {
-                const R ud = R(*slot(buf, RI::O_U + d));
+                const R ud = R(in[(RI::O_U + d) * PB]);
                 if (kInit) {
                     un[d] = ud;
                 } else if (second_order) {
-                    R v = R(*slot(buf, RI::O_K + d)) * alpha + ud;
+                    R v = R(in[(RI::O_K + d) * PB]) * alpha + ud;
 #pragma unroll
                     for (int j = 0; j < X; ++j)
-                        v += R(*slot(buf, RI::O_KK + d * X + j)) * (xn[j] - R(*slot(buf, RI::O_X + j)));
-                    const R hi = R(*slot(buf, RI::O_HI + d)), lo = R(*slot(buf, RI::O_LO + d));
+                        v += R(in[(RI::O_KK + d * X + j) * PB]) * (xn[j] - R(in[(RI::O_X + j) * PB]));
+                    const R hi = R(in[(RI::O_HI + d) * PB]), lo = R(in[(RI::O_LO + d) * PB]);
                     const R capped = (hi < v) ? hi : v;               // optim.c:755-758
                     un[d] = (lo > capped) ? lo : capped;
                 } else {
-                    un[d] = ud - R(*slot(buf, RI::O_K + d)) * alpha;          // optim.c:803-804
+                    un[d] = ud - R(in[(RI::O_K + d) * PB]) * alpha;          // optim.c:803-804
                 }
             }
 #pragma unroll
-            for (int j = 0; j < NSC; ++j) sc[j] = R(*slot(buf, RI::O_SC + j));
+            for (int j = 0; j < NSC; ++j) sc[j] = R(in[(RI::O_SC + j) * PB]);
             if (!kInit) {
                 XS* cut = cu + (size_t)t * U * B;
 #pragma unroll
@@ -372,7 +388,7 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
             if (kCost) {
                 R lam[D::Cs], c;
 #pragma unroll
-                for (int cc = 0; cc < D::C; ++cc) lam[cc] = R(*slot(buf, RI::O_LAM + cc));
+                for (int cc = 0; cc < D::C; ++cc) lam[cc] = R(in[(RI::O_LAM + cc) * PB]);
                 M::stage_cost(P, xn, un, lam, weight, sc, R(t), R(q.dt), &c);
                 total += (double)c;
             }
@@ -396,14 +412,16 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
     }
 }
 
-template <typename M, typename R, int PB, bool kInit, int kScheme, int kMinBlocks, bool kCost = false>
-__global__ void __launch_bounds__(PB * (kInit ? 1 : kAlphas), kMinBlocks)
+// NA: step sizes per problem in this launch = blockDim.y (1 initial rollout, 8 all at once, 2 / 6 the
+// two rounds of the throughput sequence)
+template <typename M, typename R, int PB, int NA, bool kInit, int kScheme, bool kCost = false>
+__global__ void __launch_bounds__(PB * NA)
 rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int a_begin, const int32_t* list) {
     extern __shared__ __align__(16) unsigned char rollout_smem[];
-    const int ai = kInit ? 0 : a_begin + threadIdx.y;      // blockDim.y = candidates of this launch
+    const int ai = kInit ? 0 : a_begin + threadIdx.y;
     if (list && blockIdx.x * PB >= *ws.pending_count) return;   // block-uniform: nothing pending here
     const int b = problem_of(list, ws.pending_count, blockIdx.x * PB + threadIdx.x, q.batch);
-    dev_rollout<M, R, kInit, kScheme, kCost>(q, ws, b < 0 ? 0 : b, ai, b >= 0, rollout_smem);
+    dev_rollout<M, R, PB, NA, kInit, kScheme, kCost>(q, ws, b < 0 ? 0 : b, ai, b >= 0, rollout_smem);
 }
 
 // ---------------------------------------------------------------------------------
