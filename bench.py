@@ -401,10 +401,13 @@ def run_ours(a):
         X_, U_, C_, REC = opt.X, opt.U, opt.C, info["deriv_compact"]
         R1 = 2                                           # candidates of the first line-search round
         two_round = a.line_search_rounds == 2 or (a.line_search_rounds == 0 and B * depth >= 16384)
+        # pure penalty (lg_mult_limit = 0, the shipped callers' setting): the multipliers are
+        # identically 0 after the multiplier update and are not read again inside update()
+        LAM = 0 if float(np.max(np.abs(np.asarray(pb.lg_mult_limit)))) == 0.0 else C_
         step_copy = 4 * (X_ + U_)        # accept: winner -> x,u and x,k -> prev_x,prev_k (read + write)
         abytes = {                       # doubles moved per (problem, stage, launch)
             # x, u, multipliers in, derivative record out (+ the accept when it is folded in)
-            "linearize": (X_ + U_) + C_ + REC if two_round else step_copy + C_ + REC,
+            "linearize": (X_ + U_) + LAM + REC if two_round else step_copy + LAM + REC,
             "accept": step_copy,
             # record + u + bounds in, K and k out
             "backward": REC + 3 * U_ + U_ * X_ + U_,
@@ -414,7 +417,7 @@ def run_ours(a):
             "stage_cost": R1 * (X_ + U_) + C_ + R1,
         }
         if two_round:                    # the rollouts add up the stage costs themselves (+ multipliers in)
-            abytes["rollout"] += C_
+            abytes["rollout"] += LAM
             abytes["stage_cost"] = 0
         sat = None
         Bs = B * depth

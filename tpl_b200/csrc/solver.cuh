@@ -98,6 +98,9 @@ struct Workspace {
     int32_t* pending;      // [B]  problems whose round-1 step sizes all failed (unordered list)
     int32_t* pending_count;// [1]
     int32_t* records_f32;  // [1]  1: the derivative records were written as fp32
+    int32_t* lam_zero;     // [B]  1: every multiplier limit of the problem is 0, so after the
+                           //      multiplier update lambda is identically 0 (pure penalty — the setting of
+                           //      all shipped callers) and need not be read
 };
 
 __host__ __device__ inline size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
@@ -121,6 +124,7 @@ __host__ __device__ inline Workspace carve(void* base, int B, int S, int t_max, 
     w.pending = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)B));
     w.pending_count = reinterpret_cast<int32_t*>(take(sizeof(int32_t)));
     w.records_f32 = reinterpret_cast<int32_t*>(take(sizeof(int32_t)));
+    w.lam_zero = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)B));
     if (total) *total = off;
     return w;
 }
@@ -258,12 +262,14 @@ __device__ __forceinline__ const double* rollout_source(const tplb_batch& q, con
 }
 
 // copies items [E0, E1) of stage t into the ring slot `dst` (this problem's column)
+// (`skip_lam`: the multipliers are known to be 0 and their ring entries were zeroed once)
 template <typename M, bool kInit, bool kCost, int PB, int E0, int E1>
 __device__ __forceinline__ void rollout_fetch_range(const tplb_batch& q, const Workspace& ws, size_t t, int b,
-                                                    int scene, double* dst) {
+                                                    int scene, double* dst, bool skip_lam) {
     if constexpr (E0 < E1) {
-        async_copy8(dst + E0 * PB, rollout_source<M, kInit, kCost, E0>(q, ws, t, b, scene));
-        rollout_fetch_range<M, kInit, kCost, PB, E0 + 1, E1>(q, ws, t, b, scene, dst);
+        if (E0 < RolloutInputs<M, kInit, kCost>::O_LAM || !skip_lam)
+            async_copy8(dst + E0 * PB, rollout_source<M, kInit, kCost, E0>(q, ws, t, b, scene));
+        rollout_fetch_range<M, kInit, kCost, PB, E0 + 1, E1>(q, ws, t, b, scene, dst, skip_lam);
     }
 }
 
@@ -271,15 +277,16 @@ __device__ __forceinline__ void rollout_fetch_range(const tplb_batch& q, const W
 // chain of comparisons is a uniform jump and every warp issues only its own copies
 template <typename M, bool kInit, bool kCost, int PB, int NA, int R = 0>
 __device__ __forceinline__ void rollout_fetch(const tplb_batch& q, const Workspace& ws, size_t t, int b, int scene,
-                                              double* dst, int yy) {
+                                              double* dst, int yy, bool skip_lam) {
     using RI = RolloutInputs<M, kInit, kCost>;
     constexpr int CH = (RI::COUNT + NA - 1) / NA;
     if constexpr (R < NA) {
         if (yy == R) {
             constexpr int E0 = R * CH, E1 = (R + 1) * CH < RI::COUNT ? (R + 1) * CH : RI::COUNT;
-            rollout_fetch_range<M, kInit, kCost, PB, (E0 < RI::COUNT ? E0 : RI::COUNT), E1>(q, ws, t, b, scene, dst);
+            rollout_fetch_range<M, kInit, kCost, PB, (E0 < RI::COUNT ? E0 : RI::COUNT), E1>(q, ws, t, b, scene, dst,
+                                                                                         skip_lam);
         } else {
-            rollout_fetch<M, kInit, kCost, PB, NA, R + 1>(q, ws, t, b, scene, dst, yy);
+            rollout_fetch<M, kInit, kCost, PB, NA, R + 1>(q, ws, t, b, scene, dst, yy, skip_lam);
         }
     }
 }
@@ -331,7 +338,16 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
 
     // ring slot `buf` of this problem: item e at ring(buf)[e * PB]
     auto ring = [&](int buf) { return stage_in + buf * (RI::COUNT * PB); };
-    auto fetch = [&](int t, int buf) { rollout_fetch<M, kInit, kCost, PB, NA>(q, ws, (size_t)t, b, scene, ring(buf), yy); };
+    const bool skip_lam = kCost && D::C > 0 && live && ws.lam_zero[b] != 0;
+    auto fetch = [&](int t, int buf) {
+        rollout_fetch<M, kInit, kCost, PB, NA>(q, ws, (size_t)t, b, scene, ring(buf), yy, skip_lam);
+    };
+    if (kCost && skip_lam && yy == 0) {                      // the first barrier of the loop publishes the zeros
+#pragma unroll
+        for (int sl = 0; sl < kRolloutSlots; ++sl)
+#pragma unroll
+            for (int cc = 0; cc < D::C; ++cc) ring(sl)[(RI::O_LAM + cc) * PB] = 0.0;
+    }
 
     R xn[X];
     if (live) {
@@ -549,6 +565,10 @@ __device__ __forceinline__ void dev_multiplier(const tplb_batch& q, const Worksp
         q.improved[b] = 0;
         q.iterations[b] = 0;
         ws.running[b] = 1;
+        bool zero = C > 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) zero = zero && q.lg_mult_limit[(size_t)c * B + b] == 0.0;
+        ws.lam_zero[b] = zero;
     }
     if (C == 0) return;
     const int scene = __ldg(q.scene_index + b);
@@ -637,9 +657,11 @@ __device__ __forceinline__ void dev_linearize(const tplb_batch& q, const Workspa
 #pragma unroll
         for (int i = 0; i < U; ++i) u[i] = R(q.u[((size_t)t * U + i) * B + b]);
     }
+    // inside update() the multipliers of a pure-penalty problem are known to be 0 (ws.lam_zero)
+    const bool lam_is_zero = !kForce && C > 0 && ws.lam_zero[b] != 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        lam[c] = R(q.lagrange_multiplier[((size_t)t * C + c) * B + b]);
+        lam[c] = lam_is_zero ? R(0) : R(q.lagrange_multiplier[((size_t)t * C + c) * B + b]);
         w[c] = R(q.barrier_weight[(size_t)c * B + b]);
     }
     load_stage_consts<M, R>(q, ws, scene, t, sc);
