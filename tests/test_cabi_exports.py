@@ -87,3 +87,36 @@ def test_product_does_not_import_the_oracle():
                     text = fd.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f"{fn} imports oracle"
                 assert "liboracle" not in text and "ilqr_oracle" not in text, fn
+
+
+def _c_layout(tmp_path, header, struct, fields):
+    """sizeof and offsetof of a header struct as a plain C compiler sees them."""
+    import subprocess
+    src = tmp_path / f"{struct}.c"
+    lines = [f'#include <stdio.h>\n#include <stddef.h>\n#include "{header}"\nint main(void) {{',
+             f'  printf("%zu\\n", sizeof({struct}));']
+    lines += [f'  printf("%zu\\n", offsetof({struct}, {f}));' for f in fields]
+    lines.append("  return 0;\n}")
+    src.write_text("\n".join(lines))
+    exe = tmp_path / f"{struct}.out"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    return int(out[0]), [int(v) for v in out[1:]]
+
+
+def test_struct_layouts_match_a_c_compiler(tmp_path):
+    """The headers are plain C99, and the ctypes mirrors have the compiler's size and offsets."""
+    inc = os.path.join(common.ROOT, "include")
+    fields = [n for n, _ in _cabi.Batch._fields_]
+    size, offs = _c_layout(tmp_path, os.path.join(inc, "tplb200.h"), "tplb_batch", fields)
+    assert size == ctypes.sizeof(_cabi.Batch)
+    assert offs == [getattr(_cabi.Batch, n).offset for n in fields]
+    fields = [n for n, _ in _cabi.ModelInfo._fields_]
+    size, offs = _c_layout(tmp_path, os.path.join(inc, "tplb200.h"), "tplb_model_info", fields)
+    assert size == ctypes.sizeof(_cabi.ModelInfo)
+    assert offs == [getattr(_cabi.ModelInfo, n).offset for n in fields]
+    from tpl_b200 import sim
+    fields = [n for n, _ in sim._Ego._fields_]
+    size, offs = _c_layout(tmp_path, os.path.join(inc, "tplb200_prep.h"), "tplb_ego", fields)
+    assert size == ctypes.sizeof(sim._Ego)
+    assert offs == [getattr(sim._Ego, n).offset for n in fields]
