@@ -128,4 +128,21 @@ struct ParamView {
     }
 };
 
+
+// ParamView whose scalar parameters sit in registers.  A kernel that walks the stages in a loop
+// and stores to global memory inside it (the rollouts) would otherwise reload every scalar in
+// every stage: the compiler cannot hoist the loads over the stores.  The generated code asks
+// for scalars by literal index, so `cached` never becomes an addressable array.
+template <typename R, int NS>
+struct CachedParamView : ParamView<R> {
+    R cached[NS > 0 ? NS : 1];
+
+    __device__ __forceinline__ void preload(const ParamView<R>& base) {
+        static_cast<ParamView<R>&>(*this) = base;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) cached[i] = base.scalar(i);
+    }
+    __device__ __forceinline__ R scalar(int i) const { return cached[i]; }
+};
+
 }  // namespace tplb

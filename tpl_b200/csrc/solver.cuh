@@ -323,7 +323,8 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
     }
     const int T = q.horizon;
     const int scene = live ? __ldg(q.scene_index + b) : 0;
-    const ParamView<R> P = param_view_scene<R>(q, scene);
+    CachedParamView<R, M::NUM_SCALARS> P;                    // scalar parameters in registers for the whole chain
+    P.preload(param_view_scene<R>(q, scene));
     const bool second_order = q.use_quadratic_terms != 0;
 
     double tens = 1.0;
