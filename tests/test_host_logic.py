@@ -118,7 +118,7 @@ def test_slots_match_reference(lateral):
 
 
 def test_no_cpu_fallback(lateral, solver_libs):
-    for call in (lateral.update, lateral.linearize, lambda: lateral.shift(1),
+    for call in (lateral.update, lateral.linearize, lambda: lateral.shift(1), lambda: lateral.shift_interp(0.5),
                  lambda: lateral.dynamics(np.zeros(2), np.zeros(1), 0, 0.1),
                  lambda: lateral.argmin_groups(2)):
         with pytest.raises(_cabi.SolverError):

@@ -26,8 +26,6 @@ device and the sm_100a library loaded.
 import copy as _copy
 import ctypes as C
 
-import contextlib
-
 import numpy as np
 import torch
 
@@ -523,10 +521,10 @@ class BatchedOptim:
         multipliers are resampled linearly, ``u`` with a zero-order hold, at ``ss + arc_len`` on the
         grid ``ss = i * step`` — per problem ``arc_len`` of shape (B,).  On the device, in place."""
         from . import prep
+        if self.device.type != "cuda":
+            raise _cabi.SolverError("shift_interp runs on a CUDA device only; there is no CPU fallback")
         T = self._T
-        with torch.cuda.device(self.device) if self.device.type == "cuda" else contextlib.nullcontext():
-            if self.device.type != "cuda":
-                raise _cabi.SolverError("shift_interp runs on a CUDA device only; there is no CPU fallback")
+        with torch.cuda.device(self.device):
             self._x[:T].copy_(prep.shift_interp_soa(self._x[:T], self.dt, arc_len, "linear"))
             self._u[:T].copy_(prep.shift_interp_soa(self._u[:T], self.dt, arc_len, "zero"))
             if self.C:
