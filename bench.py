@@ -6,14 +6,19 @@
 Workload (BASELINE.json configs[1]): 4096 independent kinematic-bicycle MPC problems
 (`trajectory_tracking_mpc_time`, X=6, U=2, C=4), N=100 stages, HEUN, 10 forced
 iLQR iterations, fp64, synthetic road / reference-path data seeded per problem.
-A *step* is one `update()` of the whole batch from the same cold start.  With N
-GPUs every rank solves its own 4096 problems (weak scaling, no data-path
-collective) and one final all_gather collects the per-group best costs.
+A *step* is one `update()` of one batch of 4096 from the same cold start.  `--in-flight D`
+(default 8) solver instances, each on its own CUDA stream, take the steps round-robin
+(tpl_b200.streaming): one batch alone cannot fill the GPU, consecutive batches overlap.
+With N GPUs every rank solves its own batches (weak scaling, no data-path collective)
+and every step ends with an all_gather of the per-group best costs.
 
-Prints ONE JSON line (see the driver contract): `value` is device-resident
-throughput, `e2e` the same through the public API with host buffers, `roofline`
-the FP64-pipe fraction of the dominant kernel, `cpu_baseline` the reference's own
-CPU solver on this host.
+Prints ONE JSON line (see the driver contract): `value` is device-resident throughput,
+`e2e` the same through the public API with pinned host buffers (uploads and downloads of
+every step inside the timed region), `roofline` the HBM fraction of the dominant kernel
+(algorithmic bytes / launch duration, timed with the same number of problems in one
+batch because kernels of different streams overlap), `roofline_step` the same for the
+whole step, `roofline_fp64` the algorithmic FP64 fraction, `cpu_baseline` the reference's
+own CPU solver on this host, `latency` the single-solve p50, `profile_shaping` row f2.
 """
 
 import argparse
