@@ -306,3 +306,27 @@ def test_batched_closed_loop_against_the_oracle_loop(prep_lib, solver_libs, orac
     print(f"closed loop, {cycles} cycles: worst deviation from the oracle loop {worst:.2e}")
     assert worst <= RTOL
     assert np.all(got[-1, :, 3] > 1.0)                       # the vehicles are driving
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/library/tpl"), reason="reference tree not mounted")
+def test_oracle_against_the_live_reference_functions():
+    """Where the reference tree is present (the build container, never the GPU box) the oracle is also
+    compared with the reference's functions run live on fresh random cases, beyond the committed
+    golden vectors."""
+    numba = pytest.importorskip("numba")  # noqa: F841
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_prep", os.path.join(GOLDEN, "make_golden_prep.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    vel = mg.reference_function(os.path.join(mg.REF, "planning", "utils.py"), "rampify_profile")
+    lat = mg.reference_function(os.path.join(mg.REF, "planning", "path_vel_decomp", "path_optim.py"),
+                                "rampify_profile")
+    for seed in range(9000, 9012):
+        c = ps.velocity_case(seed, n=120 + seed % 50, with_v0=seed % 3 != 0, with_a0=seed % 2 == 0)
+        want = vel(c["v0"], c["a0"], c["lim_v"].copy(), c["a_min"], c["a_max"], c["j_min"], c["j_max"], c["v_min"],
+                   c["step"])
+        np.testing.assert_allclose(_vel_oracle(c), want, rtol=RTOL, atol=1e-12)
+        c = ps.lateral_case(seed, n=90 + seed % 40)
+        want = lat(c["step"], c["horizon"], c["evasion_sharpness"], c["proj_distance"], c["path"], c["gap"],
+                   c["lower"], c["upper"])
+        np.testing.assert_allclose(_lat_oracle(c), want, rtol=RTOL, atol=1e-12)
