@@ -44,7 +44,7 @@ extern "C" {
 #define TPLB_API
 #endif
 
-#define TPLB_ABI_VERSION 1
+#define TPLB_ABI_VERSION 2
 #define TPLB_MAX_ARRAYS 16
 #define TPLB_LINE_SEARCH_STEPS 8          /* alpha = 10^-i, i = 0..7, optim.c:861-863 */
 #define TPLB_HORIZON_MAX 299              /* H_MAX - 1, optim.c:49, 1732 */
@@ -105,7 +105,11 @@ typedef struct {
                                           need them (least work: best when the GPU is full, i.e. large
                                           batches or several batches in flight on different streams),
                                       0 = choose by batch size (2 from 16384 problems on). */
-    int32_t reserved0;             /* must be 0 */
+    int32_t keep_records;          /* 1: the derivative records of the last linearisation stay readable through
+                                      tplb_expand_derivatives() after update().  The sequences for small
+                                      batches always keep them; the fused sweep of the throughput sequence
+                                      stores them only on request (29 extra doubles per stage and iteration
+                                      for the bicycle model). */
     double dt;                     /* dt ("step") */
     double min_rel_cost_change;    /* minRelCostChange */
 

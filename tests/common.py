@@ -29,7 +29,6 @@ from tpl_b200 import scenarios as sc   # noqa: E402
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 RTOL = 1e-9          # BASELINE.json: per-iteration controls, states and cost within 1e-9 relative (fp64)
-PLATEAU = 1e-9       # iterations whose relative cost change is below this are the round-off plateau
 
 
 # ---------------------------------------------------------------------------------
@@ -93,29 +92,17 @@ def make_case(name):
 # traces
 # ---------------------------------------------------------------------------------
 
-SCALARS = ("traj_costs", "alpha", "mu_step", "iterations", "termination_condition",
-           "improved", "trajectory_changed", "lg_iterations")
+from tpl_b200 import parity   # noqa: E402
+from tpl_b200.parity import (SCALARS, analyse, batched_problem_trace, compare_traces, rel_err,   # noqa: E402,F401
+                             same_decisions)
 
-
-def _snapshot_single(q):
-    d = {"x": np.array(q.x, dtype=np.float64).reshape(q.horizon + 1, -1),
-         "u": np.array(q.u, dtype=np.float64).reshape(q.horizon, -1)}
-    for s in SCALARS:
-        d[s] = float(getattr(q, s))
-    return d
+_snapshot_single = parity.snapshot_single
 
 
 def trace_single(factory, pb, i, iters):
     """[snapshot after max_iterations = 0..iters] for problem ``i`` solved by an
     object with the reference ``Optim`` interface (real reference or CPU oracle)."""
-    base = sc.apply_to_single(factory(), pb, i)
-    out = []
-    for s in range(iters + 1):
-        q = copy.deepcopy(base)
-        q.max_iterations = s
-        q.update()
-        out.append(_snapshot_single(q))
-    return out
+    return parity.trace_single(sc.apply_to_single(factory(), pb, i), iters)
 
 
 def derivatives_single(factory, pb, i):
@@ -140,19 +127,7 @@ def q_dim(q, what):
 def trace_batched(bopt_factory, pb, iters):
     """Same trace for the whole batch on the CUDA solver: list over s of dicts of
     (B, ...) numpy arrays."""
-    base = sc.apply_to_batched(bopt_factory(), pb)
-    out = []
-    for s in range(iters + 1):
-        q = copy.deepcopy(base)
-        q.max_iterations = s
-        q.update()
-        T = q.horizon
-        d = {"x": q.x.cpu().numpy().reshape(q.batch, T + 1, -1),
-             "u": q.u.cpu().numpy().reshape(q.batch, T, -1)}
-        for n in SCALARS:
-            d[n] = getattr(q, n).cpu().numpy().astype(np.float64)
-        out.append(d)
-    return out
+    return parity.trace_batched(sc.apply_to_batched(bopt_factory(), pb), iters)
 
 
 def derivatives_batched(bopt_factory, pb):
@@ -164,46 +139,6 @@ def derivatives_batched(bopt_factory, pb):
     for n in ("fx", "fu", "lx", "lu", "lxx", "luu", "lux", "k", "K"):
         out[n] = getattr(q, n).cpu().numpy()
     return out
-
-
-# ---------------------------------------------------------------------------------
-# comparison
-# ---------------------------------------------------------------------------------
-
-def rel_err(a, b):
-    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    scale = max(np.max(np.abs(b)), 1e-300)
-    return float(np.max(np.abs(a - b)) / scale) if a.size else 0.0
-
-
-def same_decisions(a, b):
-    return (np.isclose(a["alpha"], b["alpha"], rtol=1e-12, atol=0.0)
-            and int(a["mu_step"]) == int(b["mu_step"])
-            and int(a["iterations"]) == int(b["iterations"])
-            and int(a["termination_condition"]) == int(b["termination_condition"])
-            and int(a["improved"]) == int(b["improved"])
-            and int(a["trajectory_changed"]) == int(b["trajectory_changed"]))
-
-
-def compare_traces(test, ref, rtol=RTOL):
-    """Compare two single-problem traces.  Returns (worst relative error over the
-    compared iterations, first iteration whose decisions differ or None,
-    whether that flip happened on the round-off plateau)."""
-    worst = 0.0
-    for s, (a, b) in enumerate(zip(test, ref)):
-        if not same_decisions(a, b):
-            prev = ref[s - 1]["traj_costs"] if s else np.inf
-            on_plateau = abs(prev - b["traj_costs"]) <= PLATEAU * abs(b["traj_costs"]) or \
-                abs(a["traj_costs"] - b["traj_costs"]) <= 1e-12 * abs(b["traj_costs"])
-            return worst, s, bool(on_plateau)
-        worst = max(worst, rel_err(a["x"], b["x"]), rel_err(a["u"], b["u"]),
-                    abs(a["traj_costs"] - b["traj_costs"]) / max(abs(b["traj_costs"]), 1e-300))
-    return worst, None, False
-
-
-def batched_problem_trace(tr, i):
-    """Slice problem ``i`` out of a batched trace."""
-    return [{k: (v[i] if isinstance(v, np.ndarray) else v) for k, v in snap.items()} for snap in tr]
 
 
 # ---------------------------------------------------------------------------------

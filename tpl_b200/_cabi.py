@@ -2,7 +2,7 @@
 
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_ARRAYS = 16
 LINE_SEARCH_STEPS = 8
 HORIZON_MAX = 299
@@ -33,7 +33,7 @@ class Batch(C.Structure):
         ("opt_start", C.c_int32), ("max_iterations", C.c_int32), ("max_lg_iterations", C.c_int32),
         ("integrator_type", C.c_int32), ("use_quadratic_terms", C.c_int32),
         ("keep_previous", C.c_int32), ("precision", C.c_int32),
-        ("line_search_rounds", C.c_int32), ("reserved0", C.c_int32),
+        ("line_search_rounds", C.c_int32), ("keep_records", C.c_int32),
         ("dt", C.c_double), ("min_rel_cost_change", C.c_double),
         ("x", _D), ("u", _D), ("prev_x", _D), ("prev_k", _D), ("k", _D), ("K", _D), ("g", _D),
         ("lagrange_multiplier", _D), ("barrier_weight", _D), ("lg_mult_limit", _D),

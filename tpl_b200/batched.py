@@ -135,6 +135,48 @@ class BatchedParams:
         return d
 
 
+class HostMirror:
+    """Pinned host staging buffers of one ``BatchedOptim`` — the reference keeps its arrays in
+    host memory (numpy views of the ``Optim`` struct, optim.c:1302-1347); a batched device solve
+    needs one host->device and one device->host transfer per batch instead.
+
+    The buffers have the solver's own layout (problem index fastest), so ``opt.upload`` /
+    ``opt.download`` are plain DMA transfers without a repacking kernel; the attributes are
+    zero-copy *views* of them in the reference's shapes.  Inputs: ``x0`` (B, X), ``u0`` (B, T, U)
+    squeezed like the device views, ``scalars`` (num_scalars, S) in ``params.scalar_names`` order,
+    ``arrays[name]`` (S, L).  Results: ``x`` (B, T+1, X), ``u`` (B, T, U), ``traj_costs`` /
+    ``iterations`` / ``termination_condition`` (B,).
+    """
+
+    def __init__(self, opt):
+        B, T, X, U = opt.batch, opt.horizon, opt.X, opt.U
+        pin = dict(pin_memory=True)
+        self.horizon = T
+        # inputs: initial state and control warm start
+        self._x0 = torch.zeros((X, B), dtype=torch.float64, **pin)
+        self._u0 = torch.zeros((T, U, B), dtype=torch.float64, **pin)
+        self.x0 = self._x0.t()
+        self.u0 = opt._traj_view(self._u0, T, (U,))
+        # results
+        self._x = torch.zeros((T + 1, X, B), dtype=torch.float64, **pin)
+        self._u = torch.zeros((T, U, B), dtype=torch.float64, **pin)
+        self.x = opt._traj_view(self._x, T + 1, (X,))
+        self.u = opt._traj_view(self._u, T, (U,))
+        self.traj_costs = torch.zeros(B, dtype=torch.float64, **pin)
+        self._flags = torch.zeros((2, B), dtype=torch.int32, **pin)
+        self.iterations, self.termination_condition = self._flags[0], self._flags[1]
+        self.scalars = torch.zeros(tuple(opt._scalars.shape), dtype=torch.float64, **pin)
+        self.arrays = {n: torch.zeros(tuple(opt._arrays[i].shape), dtype=torch.float64, **pin)
+                       for n, i in opt._array_index.items()}
+
+    def upload_bytes(self):
+        return (self._x0.numel() + self._u0.numel() + self.scalars.numel()
+                + sum(a.numel() for a in self.arrays.values())) * 8
+
+    def download_bytes(self):
+        return (self._x.numel() + self._u.numel() + self.traj_costs.numel()) * 8 + self._flags.numel() * 4
+
+
 class ProblemView:
     """``opt[i]``: one problem with exactly the reference's shapes."""
 
@@ -166,7 +208,7 @@ class BatchedOptim:
     _STATUS = ("traj_costs", "alpha", "mu", "iterations", "lg_iterations", "mu_step",
                "trajectory_changed", "improved", "termination_condition")
     _SETTINGS = ("dt", "max_iterations", "max_lg_iterations", "min_rel_cost_change",
-                 "opt_start", "use_quadratic_terms", "integrator_type", "keep_previous", "precision",
+                 "opt_start", "use_quadratic_terms", "integrator_type", "keep_previous", "keep_records", "precision",
                  "line_search_rounds")
 
     def __init__(self, lib_path, batch=1, scenes=None, horizon_max=None, device=None):
@@ -225,7 +267,8 @@ class BatchedOptim:
         self.use_quadratic_terms = True
         self.opt_start = 0
         self.integrator_type = EULER
-        self.keep_previous = True
+        self.keep_previous = True          # maintain prev_x / prev_k on accepted steps (optim.c:844-845)
+        self.keep_records = True           # fx..lux readable after update() (always true for small batches)
         self.precision = "fp64"            # "fp32": kernels compute in single precision
         self.line_search_rounds = 0        # 0 auto, 1 all step sizes at once, 2 in two rounds (tplb200.h)
         self.params = BatchedParams(self)
@@ -360,7 +403,10 @@ class BatchedOptim:
                 view.copy_(_fit(_source(v), view), non_blocking=True)
         elif n in self._STATUS:
             t = self._status[n]
-            t.copy_(_as_tensor(v, self.device, t.dtype).expand_as(t))
+            if isinstance(v, (int, float)):                       # no host tensor: also legal inside a CUDA graph
+                t.fill_(v)
+            else:
+                t.copy_(_as_tensor(v, self.device, t.dtype).expand_as(t))
         else:
             object.__setattr__(self, n, v)
 
@@ -375,6 +421,34 @@ class BatchedOptim:
     def set_initial_state(self, x0):
         """``opt.x[:, 0] = x0`` for host or device ``x0`` of shape (B, X)."""
         self._x[0].copy_(_source(x0).expand(self.batch, self.X).t(), non_blocking=True)
+
+    # -- host staging (HostMirror) -------------------------------------------------------------
+    def host_mirror(self):
+        """Pinned host buffers for this solver's inputs and results (see ``HostMirror``)."""
+        return HostMirror(self)
+
+    def upload(self, m, params=True):
+        """Initial state, control warm start and (optionally) all parameters from the pinned
+        mirror ``m``: contiguous asynchronous copies on the current stream."""
+        self._require_cuda("upload()")
+        T = self._T
+        self._x[0].copy_(m._x0, non_blocking=True)
+        self._u[:T].copy_(m._u0, non_blocking=True)
+        if params:
+            self._scalars.copy_(m.scalars, non_blocking=True)
+            for n, i in self._array_index.items():
+                self._arrays[i].copy_(m.arrays[n], non_blocking=True)
+
+    def download(self, m):
+        """Trajectories, costs, iteration counts and termination flags into the pinned mirror
+        ``m`` (asynchronous; synchronise the stream before reading them on the host)."""
+        self._require_cuda("download()")
+        T = self._T
+        m._x.copy_(self._x[:T + 1], non_blocking=True)
+        m._u.copy_(self._u[:T], non_blocking=True)
+        m.traj_costs.copy_(self._status["traj_costs"], non_blocking=True)
+        m._flags[0].copy_(self._status["iterations"], non_blocking=True)
+        m._flags[1].copy_(self._status["termination_condition"], non_blocking=True)
 
     # -- C ABI plumbing ---------------------------------------------------------------
     def _ensure_workspace(self):
@@ -394,6 +468,7 @@ class BatchedOptim:
         q.integrator_type = int(self.integrator_type)
         q.use_quadratic_terms = int(bool(self.use_quadratic_terms))
         q.keep_previous = int(bool(self.keep_previous))
+        q.keep_records = int(bool(self.keep_records))
         q.precision = {"fp64": 0, "fp32": 1}[self.precision]
         q.line_search_rounds = int(self.line_search_rounds)
         q.dt = float(self.dt)
@@ -427,12 +502,16 @@ class BatchedOptim:
         current CUDA stream."""
         self._require_cuda("update()")
         with torch.cuda.device(self.device):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
             q = self._descriptor()
-            _cabi.check(self._lib, self._lib.tplb_update(C.byref(q), self._stream()), "tplb_update")
-            e1.record()
-            self._events = (e0, e1)
+            if torch.cuda.is_current_stream_capturing():   # inside a CUDA graph: no timing events
+                _cabi.check(self._lib, self._lib.tplb_update(C.byref(q), self._stream()), "tplb_update")
+                self._events = None
+            else:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _cabi.check(self._lib, self._lib.tplb_update(C.byref(q), self._stream()), "tplb_update")
+                e1.record()
+                self._events = (e0, e1)
             self._deriv_stale = True
 
     def update_profiled(self):

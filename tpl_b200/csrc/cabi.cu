@@ -52,7 +52,7 @@ int validate(const tplb_batch* q) {
         return fail(TPLB_E_UNSUPPORTED, "integrator_type must be EULER, HEUN or RK4");
     if (q->precision != TPLB_FP64 && q->precision != TPLB_FP32)
         return fail(TPLB_E_UNSUPPORTED, "precision must be TPLB_FP64 or TPLB_FP32");
-    if (q->line_search_rounds < 0 || q->line_search_rounds > 2 || q->reserved0 != 0)
+    if (q->line_search_rounds < 0 || q->line_search_rounds > 2)
         return fail(TPLB_E_ARG, "line_search_rounds must be 0, 1 or 2");
     if (!q->x || !q->u || !q->k || !q->K || !q->u_min || !q->u_max || !q->traj_costs || !q->alpha ||
         !q->mu || !q->iterations || !q->lg_iterations || !q->mu_step || !q->trajectory_changed ||
@@ -226,6 +226,10 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
     //                the HBM roofline) in front of a plain linearize.
     const bool throughput = throughput_sequence(q);
     const bool fold_accept = !throughput;
+    // throughput sequence of the second-order solver: one fused kernel per iteration in front of
+    // the rollouts (TPLB_NO_FUSED_SWEEP=1 in the environment keeps the three separate kernels, for A/B runs)
+    static const bool no_fused = std::getenv("TPLB_NO_FUSED_SWEEP") != nullptr;
+    const bool fused_sweep = throughput && q.use_quadratic_terms && !no_fused;
 
     prof.before();
     tplb::stage_constants_kernel<Model><<<dim3((S + sb - 1) / sb, T + 1), sb, 0, st>>>(q, ws);
@@ -244,16 +248,25 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
         tplb::multiplier_kernel<Model, R><<<dim3(sgx, Model::C > 0 ? T : 1), sb, 0, st>>>(q, ws);
         prof.after(TPLB_K_MULTIPLIER);
         for (int s = 0; s < q.max_iterations; ++s) {
-            prof.before();
-            if (s == 0 || !fold_accept) tplb::linearize_kernel<Model, R, false, false><<<dim3(sgx, T), sb, 0, st>>>(q, ws);
-            else tplb::linearize_kernel<Model, R, false, true><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
-            prof.after(TPLB_K_LINEARIZE);
-            prof.before();
-            if (q.use_quadratic_terms)
-                tplb::backward_kernel<Model, R><<<pgrid, pb, 0, st>>>(q, ws, s);
-            else
-                tplb::backward_first_order_kernel<Model, R><<<pgrid, pb, 0, st>>>(q, ws, s);
-            prof.after(TPLB_K_BACKWARD);
+            if (fused_sweep) {
+                // linearise + Riccati in one pass over the stages; installs the step the previous
+                // line search accepted on the way (no accept / linearize / record traffic)
+                prof.before();
+                if (s == 0) tplb::sweep_kernel<Model, R, false><<<pgrid, pb, 0, st>>>(q, ws, s);
+                else tplb::sweep_kernel<Model, R, true><<<pgrid, pb, 0, st>>>(q, ws, s);
+                prof.after(TPLB_K_BACKWARD);
+            } else {
+                prof.before();
+                if (s == 0 || !fold_accept) tplb::linearize_kernel<Model, R, false, false><<<dim3(sgx, T), sb, 0, st>>>(q, ws);
+                else tplb::linearize_kernel<Model, R, false, true><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
+                prof.after(TPLB_K_LINEARIZE);
+                prof.before();
+                if (q.use_quadratic_terms)
+                    tplb::backward_kernel<Model, R><<<pgrid, pb, 0, st>>>(q, ws, s);
+                else
+                    tplb::backward_first_order_kernel<Model, R><<<pgrid, pb, 0, st>>>(q, ws, s);
+                prof.after(TPLB_K_BACKWARD);
+            }
 
             if (throughput) {
                 // round 1: alpha = 1, 0.1; round 2: the other six for the problems still pending
@@ -290,7 +303,7 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
                 tplb::select_kernel<PB, 2><<<(B + PB - 1) / PB, dim3(PB, R2), 0, st>>>(q, ws);
                 prof.after(TPLB_K_SELECT);
             }
-            if (!fold_accept && s + 1 < q.max_iterations) {
+            if (!fold_accept && !fused_sweep && s + 1 < q.max_iterations) {
                 prof.before();
                 tplb::accept_kernel<Model, SC><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
                 prof.after(TPLB_K_ACCEPT);

@@ -760,6 +760,163 @@ __device__ __forceinline__ void madd(R& acc, int slot, R a, R v) {
 }
 
 // ---------------------------------------------------------------------------------
+// one stage of the Riccati recursion (optim.c:926-985): Q terms from the compact record `rec`
+// of the stage and the value function of the next one, gains, box limits on the feed-forward
+// step, value function of this stage.  Everything in registers; shared by the stand-alone
+// backward sweep and the fused linearise+sweep, so both round identically.
+// ---------------------------------------------------------------------------------
+template <typename M, typename R>
+__device__ __forceinline__ void riccati_stage(const R (&rec)[Dims<M>::COMPACT], R (&Vx)[M::X], R (&Vxx)[M::X][M::X],
+                                              R mu, const R (&ub)[M::U], const R (&hib)[M::U],
+                                              const R (&lob)[M::U], R (&k)[M::U], R (&K)[M::U][M::X]) {
+    using D = Dims<M>;
+    constexpr int X = D::X, U = D::U;
+    // dense entry e of the record: stored value, or the constant the structure says
+    auto val = [&](int e) {
+        const int s = M::deriv_slot(e);
+        return s >= 0 ? rec[s] : (s == -2 ? R(1) : R(0));
+    };
+#define A_(i, j) val(D::OFF_FX + (i) * X + (j))
+#define SA_(i, j) M::deriv_slot(D::OFF_FX + (i) * X + (j))
+#define B_(i, j) val(D::OFF_FU + (i) * U + (j))
+#define SB_(i, j) M::deriv_slot(D::OFF_FU + (i) * U + (j))
+
+    R Qx[X], Qu[U], Qxx[X][X], Quu[U][U], Qux[U][X];
+    R VA[X][X], VB[X][U];
+
+#pragma unroll
+    for (int i = 0; i < X; ++i) {                        // Qx = lx + A' Vx
+        R acc = R(0);
+#pragma unroll
+        for (int r = 0; r < X; ++r) madd(acc, SA_(r, i), A_(r, i), Vx[r]);
+        Qx[i] = val(D::OFF_LX + i) + acc;
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i) {                        // Qu = lu + B' Vx
+        R acc = R(0);
+#pragma unroll
+        for (int r = 0; r < X; ++r) madd(acc, SB_(r, i), B_(r, i), Vx[r]);
+        Qu[i] = val(D::OFF_LU + i) + acc;
+    }
+#pragma unroll
+    for (int i = 0; i < X; ++i) {                        // VA = Vxx A, VB = Vxx B
+#pragma unroll
+        for (int j = 0; j < X; ++j) {
+            R acc = R(0);
+#pragma unroll
+            for (int r = 0; r < X; ++r) madd(acc, SA_(r, j), A_(r, j), Vxx[i][r]);
+            VA[i][j] = acc;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            R acc = R(0);
+#pragma unroll
+            for (int r = 0; r < X; ++r) madd(acc, SB_(r, j), B_(r, j), Vxx[i][r]);
+            VB[i][j] = acc;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < X; ++i)                          // Qxx = lxx + A' VA (lower triangle mirrored)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            R acc = R(0);
+#pragma unroll
+            for (int r = 0; r < X; ++r) madd(acc, SA_(r, i), A_(r, i), VA[r][j]);
+            Qxx[i][j] = acc;
+            Qxx[j][i] = acc;
+        }
+#pragma unroll
+    for (int i = 0; i < X; ++i)
+#pragma unroll
+        for (int j = 0; j < X; ++j) Qxx[i][j] = val(D::OFF_LXX + i * X + j) + Qxx[i][j];
+#pragma unroll
+    for (int i = 0; i < U; ++i)                          // Quu = luu + B' VB (lower triangle mirrored)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            R acc = R(0);
+#pragma unroll
+            for (int r = 0; r < X; ++r) madd(acc, SB_(r, i), B_(r, i), VB[r][j]);
+            Quu[i][j] = acc;
+            Quu[j][i] = acc;
+        }
+#pragma unroll
+    for (int i = 0; i < U; ++i)
+#pragma unroll
+        for (int j = 0; j < U; ++j) Quu[i][j] = val(D::OFF_LUU + i * U + j) + Quu[i][j];
+#pragma unroll
+    for (int i = 0; i < U; ++i)                          // Qux = lux + B' VA
+#pragma unroll
+        for (int j = 0; j < X; ++j) {
+            R acc = R(0);
+#pragma unroll
+            for (int r = 0; r < X; ++r) madd(acc, SB_(r, i), B_(r, i), VA[r][j]);
+            Qux[i][j] = val(D::OFF_LUX + i * X + j) + acc;
+        }
+#undef A_
+#undef SA_
+#undef B_
+#undef SB_
+
+    control_gains<X, U, R>(Quu, Qu, Qux, mu, k, K);
+
+    // box limits on the feed-forward step (optim.c:950-963)
+#pragma unroll
+    for (int d = 0; d < U; ++d) {
+        const R cand = ub[d] + k[d];
+        if (cand > hib[d]) {
+            k[d] = hib[d] - ub[d];
+#pragma unroll
+            for (int j = 0; j < X; ++j) K[d][j] = R(0);
+        }
+        if (cand < lob[d]) {
+            k[d] = lob[d] - ub[d];
+#pragma unroll
+            for (int j = 0; j < X; ++j) K[d][j] = R(0);
+        }
+    }
+
+    // value function (optim.c:965-984)
+    R KtQux[X][X], KtQuu[X][U];
+#pragma unroll
+    for (int i = 0; i < X; ++i) {
+#pragma unroll
+        for (int j = 0; j < X; ++j) {
+            R acc = R(0);
+#pragma unroll
+            for (int c = 0; c < U; ++c) acc += K[c][i] * Qux[c][j];
+            KtQux[i][j] = acc;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            R acc = R(0);
+#pragma unroll
+            for (int c = 0; c < U; ++c) acc += K[c][i] * Quu[c][j];
+            KtQuu[i][j] = acc;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < X; ++i)
+#pragma unroll
+        for (int j = 0; j < X; ++j) {
+            R v = KtQux[j][i] + KtQux[i][j];
+#pragma unroll
+            for (int c = 0; c < U; ++c) v += KtQuu[i][c] * K[c][j];
+            Vxx[i][j] = v + Qxx[i][j];
+        }
+#pragma unroll
+    for (int i = 0; i < X; ++i) {
+        R v = R(0);
+#pragma unroll
+        for (int c = 0; c < U; ++c) v += KtQuu[i][c] * k[c];
+#pragma unroll
+        for (int c = 0; c < U; ++c) v += K[c][i] * Qu[c];
+#pragma unroll
+        for (int c = 0; c < U; ++c) v += Qux[c][i] * k[c];
+        Vx[i] = v + Qx[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // backward Riccati sweep — thread per problem, value function in registers.
 // The next stage's compact record is prefetched while the current one is processed.
 // ---------------------------------------------------------------------------------
@@ -809,152 +966,13 @@ __device__ __forceinline__ void dev_backward(const tplb_batch& q, const Workspac
         for (int d = 0; d < U; ++d) { ub[d] = nub[d]; hib[d] = nhib[d]; lob[d] = nlob[d]; }
         if (t > 0) fetch(t - 1, nxt, nub, nhib, nlob);
 
-        // dense entry e of the record: stored value, or the constant the structure says
-        auto val = [&](int e) {
-            const int s = M::deriv_slot(e);
-            return s >= 0 ? rec[s] : (s == -2 ? R(1) : R(0));
-        };
-#define A_(i, j) val(D::OFF_FX + (i) * X + (j))
-#define SA_(i, j) M::deriv_slot(D::OFF_FX + (i) * X + (j))
-#define B_(i, j) val(D::OFF_FU + (i) * U + (j))
-#define SB_(i, j) M::deriv_slot(D::OFF_FU + (i) * U + (j))
-
-        R Qx[X], Qu[U], Qxx[X][X], Quu[U][U], Qux[U][X];
-        R VA[X][X], VB[X][U];
-
-#pragma unroll
-        for (int i = 0; i < X; ++i) {                        // Qx = lx + A' Vx
-            R acc = R(0);
-#pragma unroll
-            for (int r = 0; r < X; ++r) madd(acc, SA_(r, i), A_(r, i), Vx[r]);
-            Qx[i] = val(D::OFF_LX + i) + acc;
-        }
-#pragma unroll
-        for (int i = 0; i < U; ++i) {                        // Qu = lu + B' Vx
-            R acc = R(0);
-#pragma unroll
-            for (int r = 0; r < X; ++r) madd(acc, SB_(r, i), B_(r, i), Vx[r]);
-            Qu[i] = val(D::OFF_LU + i) + acc;
-        }
-#pragma unroll
-        for (int i = 0; i < X; ++i) {                        // VA = Vxx A, VB = Vxx B
-#pragma unroll
-            for (int j = 0; j < X; ++j) {
-                R acc = R(0);
-#pragma unroll
-                for (int r = 0; r < X; ++r) madd(acc, SA_(r, j), A_(r, j), Vxx[i][r]);
-                VA[i][j] = acc;
-            }
-#pragma unroll
-            for (int j = 0; j < U; ++j) {
-                R acc = R(0);
-#pragma unroll
-                for (int r = 0; r < X; ++r) madd(acc, SB_(r, j), B_(r, j), Vxx[i][r]);
-                VB[i][j] = acc;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < X; ++i)                          // Qxx = lxx + A' VA (lower triangle mirrored)
-#pragma unroll
-            for (int j = 0; j <= i; ++j) {
-                R acc = R(0);
-#pragma unroll
-                for (int r = 0; r < X; ++r) madd(acc, SA_(r, i), A_(r, i), VA[r][j]);
-                Qxx[i][j] = acc;
-                Qxx[j][i] = acc;
-            }
-#pragma unroll
-        for (int i = 0; i < X; ++i)
-#pragma unroll
-            for (int j = 0; j < X; ++j) Qxx[i][j] = val(D::OFF_LXX + i * X + j) + Qxx[i][j];
-#pragma unroll
-        for (int i = 0; i < U; ++i)                          // Quu = luu + B' VB (lower triangle mirrored)
-#pragma unroll
-            for (int j = 0; j <= i; ++j) {
-                R acc = R(0);
-#pragma unroll
-                for (int r = 0; r < X; ++r) madd(acc, SB_(r, i), B_(r, i), VB[r][j]);
-                Quu[i][j] = acc;
-                Quu[j][i] = acc;
-            }
-#pragma unroll
-        for (int i = 0; i < U; ++i)
-#pragma unroll
-            for (int j = 0; j < U; ++j) Quu[i][j] = val(D::OFF_LUU + i * U + j) + Quu[i][j];
-#pragma unroll
-        for (int i = 0; i < U; ++i)                          // Qux = lux + B' VA
-#pragma unroll
-            for (int j = 0; j < X; ++j) {
-                R acc = R(0);
-#pragma unroll
-                for (int r = 0; r < X; ++r) madd(acc, SB_(r, i), B_(r, i), VA[r][j]);
-                Qux[i][j] = val(D::OFF_LUX + i * X + j) + acc;
-            }
-#undef A_
-#undef SA_
-#undef B_
-#undef SB_
-
         R k[U], K[U][X];
-        control_gains<X, U, R>(Quu, Qu, Qux, mu, k, K);
-
-        // box limits on the feed-forward step (optim.c:950-963)
+        riccati_stage<M, R>(rec, Vx, Vxx, R(mu), ub, hib, lob, k, K);
 #pragma unroll
         for (int d = 0; d < U; ++d) {
-            const R cand = ub[d] + k[d];
-            if (cand > hib[d]) {
-                k[d] = hib[d] - ub[d];
-#pragma unroll
-                for (int j = 0; j < X; ++j) K[d][j] = R(0);
-            }
-            if (cand < lob[d]) {
-                k[d] = lob[d] - ub[d];
-#pragma unroll
-                for (int j = 0; j < X; ++j) K[d][j] = R(0);
-            }
             q.k[((size_t)t * U + d) * B + b] = k[d];
 #pragma unroll
             for (int j = 0; j < X; ++j) q.K[((size_t)t * U * X + d * X + j) * B + b] = K[d][j];
-        }
-
-        // value function (optim.c:965-984)
-        R KtQux[X][X], KtQuu[X][U];
-#pragma unroll
-        for (int i = 0; i < X; ++i) {
-#pragma unroll
-            for (int j = 0; j < X; ++j) {
-                R acc = R(0);
-#pragma unroll
-                for (int c = 0; c < U; ++c) acc += K[c][i] * Qux[c][j];
-                KtQux[i][j] = acc;
-            }
-#pragma unroll
-            for (int j = 0; j < U; ++j) {
-                R acc = R(0);
-#pragma unroll
-                for (int c = 0; c < U; ++c) acc += K[c][i] * Quu[c][j];
-                KtQuu[i][j] = acc;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < X; ++i)
-#pragma unroll
-            for (int j = 0; j < X; ++j) {
-                R v = KtQux[j][i] + KtQux[i][j];
-#pragma unroll
-                for (int c = 0; c < U; ++c) v += KtQuu[i][c] * K[c][j];
-                Vxx[i][j] = v + Qxx[i][j];
-            }
-#pragma unroll
-        for (int i = 0; i < X; ++i) {
-            R v = R(0);
-#pragma unroll
-            for (int c = 0; c < U; ++c) v += KtQuu[i][c] * k[c];
-#pragma unroll
-            for (int c = 0; c < U; ++c) v += K[c][i] * Qu[c];
-#pragma unroll
-            for (int c = 0; c < U; ++c) v += Qux[c][i] * k[c];
-            Vx[i] = v + Qx[i];
         }
     }
 }
@@ -966,6 +984,178 @@ backward_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteratio
     if (b == 0) *ws.pending_count = 0;           // the line search of this iteration starts empty
     if (b >= q.batch) return;
     dev_backward<M, R>(q, ws, b, iteration);
+}
+
+// ---------------------------------------------------------------------------------
+// fused linearise + Riccati sweep — the throughput sequence's replacement for
+// accept_kernel + linearize_kernel + backward_kernel.  Thread per problem, t = T-1 .. 0:
+//   * the trajectory is read straight from the candidate the previous line search accepted
+//     (ws.winner) and installed into x, u on the way (optim.c:844-848) — no separate copy pass;
+//   * the derivative record of stage t is evaluated in registers and consumed by the Riccati
+//     step of the same stage (optim.c:896-985) — it never travels through HBM
+//     (q.keep_records != 0: it is also stored for the fx..lux views);
+//   * gains K, k are the only per-stage output.
+// Per (problem, stage): x, u (8) + box limits (4) [+ multipliers] in, x, u (8) + K, k (14) out,
+// instead of 32 (accept) + 37 (linearize) + 49 (backward) doubles.
+// kAccept == false: first iteration of an inner loop (nothing to install).
+// A problem that stopped in the previous iteration only installs its last accepted step.
+// Linearising again after a failed line search (trajectory_changed == 0, optim.c:896 skips
+// it) reproduces the stored record bit for bit: same inputs, same code.
+// ---------------------------------------------------------------------------------
+template <typename M, typename R, typename PV>
+__device__ __forceinline__ void stage_record(const PV& P, const R* x, const R* u, const R* lam, const R* w,
+                                             const R* sc, R t, R dt, R (&rec)[Dims<M>::COMPACT]) {
+    using D = Dims<M>;
+    R blk[D::DENSE];
+    M::linearize(P, x, u, lam, w, sc, t, dt, blk + D::OFF_FX, blk + D::OFF_FU, blk + D::OFF_LX, blk + D::OFF_LU,
+                 blk + D::OFF_LXX, blk + D::OFF_LUU, blk + D::OFF_LUX);
+#pragma unroll
+    for (int e = 0; e < D::DENSE; ++e)
+        if (M::deriv_owner(e)) rec[M::deriv_slot(e)] = blk[e];
+}
+
+template <typename M, typename R, bool kAccept>
+__device__ __forceinline__ void dev_sweep(const tplb_batch& q, const Workspace& ws, int b, int iteration) {
+    using D = Dims<M>;
+    using S = scratch_t<R>;
+    constexpr int X = D::X, U = D::U, C = D::C, NC = D::COMPACT, NSC = D::NSC;
+    const int B = q.batch, T = q.horizon;
+    const int win = kAccept ? ws.winner[b] : -1;
+    const bool run = ws.running[b] != 0;
+    if (!run && win < 0) return;
+    const bool install = win >= 0;
+    const S* cx = scratch<S>(ws.cand_x) + (size_t)(install ? win : 0) * (q.t_max + 1) * X * B + b;
+    const S* cu = scratch<S>(ws.cand_u) + (size_t)(install ? win : 0) * q.t_max * U * B + b;
+    double* qx = q.x + b;
+    double* qu = q.u + b;
+    const bool keep = install && q.keep_previous != 0;
+
+    // component i of stage t of the trajectory this iteration linearises about
+    auto load_x = [&](int t, int i) -> R {
+        const size_t idx = ((size_t)t * X + i) * B;
+        if constexpr (std::is_same<S, double>::value) return R((install ? cx : qx)[idx]);
+        else return install ? R(cx[idx]) : R(qx[idx]);
+    };
+    auto load_u = [&](int t, int d) -> R {
+        const size_t idx = ((size_t)t * U + d) * B;
+        if constexpr (std::is_same<S, double>::value) return R((install ? cu : qu)[idx]);
+        else return install ? R(cu[idx]) : R(qu[idx]);
+    };
+    // the accepted step becomes the trajectory (optim.c:844-848)
+    auto install_x = [&](int t, const R* x) {
+        if (!install) return;
+#pragma unroll
+        for (int i = 0; i < X; ++i) {
+            const size_t idx = ((size_t)t * X + i) * B;
+            if (keep) q.prev_x[idx + b] = qx[idx];
+            qx[idx] = (double)x[i];
+        }
+    };
+    auto install_u = [&](int t, const R* u) {
+        if (!install) return;
+#pragma unroll
+        for (int d = 0; d < U; ++d) {
+            const size_t idx = ((size_t)t * U + d) * B;
+            if (keep) q.prev_k[idx + b] = q.k[idx + b];
+            qu[idx] = (double)u[d];
+        }
+    };
+
+    if (!run) {                                  // stopped in the previous iteration: install only
+        for (int t = 0; t <= T; ++t) {
+            R x[X], u[U];
+#pragma unroll
+            for (int i = 0; i < X; ++i) x[i] = load_x(t, i);
+            install_x(t, x);
+            if (t < T) {
+#pragma unroll
+                for (int d = 0; d < U; ++d) u[d] = load_u(t, d);
+                install_u(t, u);
+            }
+        }
+        return;
+    }
+
+    q.iterations[b] = iteration + 1;             // optim.c:894
+    ws.counters[b] += q.trajectory_changed[b] ? 1 : 0;
+    ws.counters[(size_t)B + b] += 1;
+    q.trajectory_changed[b] = 0;                 // optim.c:911
+    const int scene = __ldg(q.scene_index + b);
+    const ParamView<R> P = param_view_scene<R>(q, scene);
+    const R mu = R(q.mu[b]);
+    const R dt = R(q.dt);
+    const bool lam_is_zero = C > 0 && ws.lam_zero[b] != 0;
+    R w[D::Cs];
+#pragma unroll
+    for (int c = 0; c < C; ++c) w[c] = R(q.barrier_weight[(size_t)c * B + b]);
+
+    R Vx[X], Vxx[X][X];
+    {
+        R xT[X], sc[D::NSCs];
+#pragma unroll
+        for (int i = 0; i < X; ++i) xT[i] = load_x(T, i);
+        install_x(T, xT);
+        load_stage_consts<M, R>(q, ws, scene, T, sc);
+        M::end_derivatives(P, xT, sc, R(T), dt, Vx, &Vxx[0][0]);
+    }
+
+    // the trajectory of stage t is fetched one stage ahead (HBM latency); the stage constants (one
+    // set per scene, L1/L2 resident) and the multipliers are read where the stage starts
+    R nx[X], nu[U], nhi[U], nlo[U];
+    auto fetch = [&](int t) {
+#pragma unroll
+        for (int i = 0; i < X; ++i) nx[i] = load_x(t, i);
+#pragma unroll
+        for (int d = 0; d < U; ++d) {
+            const size_t idx = ((size_t)t * U + d) * B + b;
+            nu[d] = load_u(t, d);
+            nhi[d] = R(q.u_max[idx]);
+            nlo[d] = R(q.u_min[idx]);
+        }
+    };
+    fetch(T - 1);
+
+    for (int t = T - 1; t >= 0; --t) {
+        R x[X], u[U], hi[U], lo[U], lam[D::Cs], sc[D::NSCs];
+#pragma unroll
+        for (int i = 0; i < X; ++i) x[i] = nx[i];
+#pragma unroll
+        for (int d = 0; d < U; ++d) { u[d] = nu[d]; hi[d] = nhi[d]; lo[d] = nlo[d]; }
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            lam[c] = lam_is_zero ? R(0) : R(q.lagrange_multiplier[((size_t)t * C + c) * B + b]);
+        load_stage_consts<M, R>(q, ws, scene, t, sc);
+        if (t > 0) fetch(t - 1);
+        install_x(t, x);
+        install_u(t, u);                         // (reads the previous gains before they are overwritten)
+
+        R rec[NC];
+        stage_record<M, R>(P, x, u, lam, w, sc, R(t), dt, rec);
+        if (q.keep_records) {
+            S* out = scratch<S>(ws.deriv) + (size_t)t * NC * B + b;
+#pragma unroll
+            for (int s = 0; s < M::DERIV_COMPACT; ++s) __stcs(out + (size_t)s * B, (S)rec[s]);
+        }
+
+        R k[U], K[U][X];
+        riccati_stage<M, R>(rec, Vx, Vxx, mu, u, hi, lo, k, K);
+#pragma unroll
+        for (int d = 0; d < U; ++d) {
+            q.k[((size_t)t * U + d) * B + b] = k[d];
+#pragma unroll
+            for (int j = 0; j < X; ++j) q.K[((size_t)t * U * X + d * X + j) * B + b] = K[d][j];
+        }
+    }
+    if (q.keep_records && b == 0) *ws.records_f32 = sizeof(S) == sizeof(float);
+}
+
+template <typename M, typename R, bool kAccept>
+__global__ void __launch_bounds__(128)
+sweep_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteration) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) *ws.pending_count = 0;           // the line search of this iteration starts empty
+    if (b >= q.batch) return;
+    dev_sweep<M, R, kAccept>(q, ws, b, iteration);
 }
 
 // gradient-only sweep (optim.c:1038-1076): costate recursion, clipped descent direction

@@ -30,6 +30,7 @@ class _Slot:
         self.stream = stream
         self.done = torch.cuda.Event()
         self._ctx = None
+        self.graph = None
 
     def __enter__(self):
         self._ctx = torch.cuda.stream(self.stream)
@@ -40,6 +41,22 @@ class _Slot:
         self.done.record(self.stream)
         ctx, self._ctx = self._ctx, None
         return ctx.__exit__(*exc)
+
+    def capture(self, body):
+        """Record everything ``body(slot)`` enqueues (uploads, ``update()``, downloads — fixed
+        buffers only) into a CUDA graph of this slot; ``replay()`` then re-issues the whole step
+        with one launch.  An ``update()`` is 50-80 kernel launches: enqueued one by one, the host
+        limits how many batches can be in flight."""
+        torch.cuda.synchronize(self.stream.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self.stream):
+            body(self)
+        self.graph = g
+        return g
+
+    def replay(self):
+        with self:
+            self.graph.replay()
 
     def wait(self):
         """Block the host until everything enqueued on this slot has finished (needed before
@@ -54,7 +71,12 @@ class SolverPipeline:
         if not torch.cuda.is_available():
             raise RuntimeError("SolverPipeline needs a CUDA device; there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.slots = [_Slot(i, factory(), torch.cuda.Stream(self.device)) for i in range(depth)]
+        self.slots = []
+        cur = torch.cuda.current_stream(self.device)
+        for i in range(depth):
+            stream = torch.cuda.Stream(self.device)
+            self.slots.append(_Slot(i, factory(), stream))
+            stream.wait_stream(cur)        # the constructor's fills ran on the current stream
         self._n = 0
 
     def __len__(self):
