@@ -110,6 +110,13 @@ typedef struct {
                                       batches always keep them; the fused sweep of the throughput sequence
                                       stores them only on request (29 extra doubles per stage and iteration
                                       for the bicycle model). */
+    int32_t single_launch;         /* the whole update() in ONE launch, one thread block per problem, the problem
+                                      resident in shared memory (csrc/solo.cuh) — the path for a single
+                                      planning / control cycle or a handful of candidates:
+                                      0 = automatic (small fp64 second-order batches that fit shared memory),
+                                      1 = always (TPLB_E_UNSUPPORTED if the problem does not fit), -1 = never.
+                                      Results are identical to the batched launch sequences. */
+    int32_t reserved0;             /* must be 0 */
     double dt;                     /* dt ("step") */
     double min_rel_cost_change;    /* minRelCostChange */
 
@@ -160,6 +167,11 @@ typedef struct {
     /* optional: dense derivative records [t_max][deriv_stride][B] in the reference's layout
      * fx|fu|lx|lu|lxx|luu|lux (row-major each); written only by tplb_expand_derivatives() */
     double* deriv_dense;
+
+    /* optional per-problem horizon T_b [B], 1 <= T_b <= horizon (NULL: `horizon` for every problem).  Each
+     * reference Optim object owns its T (optim.c:508-622; PathOptim sets it every cycle from the length of
+     * the local map, path_optim.py:126); stages t >= T_b of problem b are neither read nor written. */
+    const int32_t* horizons;
 } tplb_batch;
 
 TPLB_API int32_t tplb_abi_version(void);
@@ -189,14 +201,15 @@ enum {
     TPLB_K_ROLLOUT_INIT = 1,  /* rollout_kernel<init> + stage_cost_kernel + init_cost_kernel */
     TPLB_K_MULTIPLIER = 2,    /* multiplier_kernel                                         */
     TPLB_K_LINEARIZE = 3,     /* linearize_kernel                                          */
-    TPLB_K_BACKWARD = 4,      /* backward_kernel                                           */
+    TPLB_K_BACKWARD = 4,      /* backward_kernel, or sweep_kernel (linearise + Riccati fused) */
     TPLB_K_ROLLOUT = 5,       /* rollout_kernel<line search>: the step-size candidates     */
     TPLB_K_STAGE_COST = 6,    /* stage_cost_kernel on the candidates (rounds 1 and 2)      */
     TPLB_K_SELECT = 7,        /* select_kernel (rounds 1 and 2)                            */
     TPLB_K_ACCEPT = 8,        /* accept_kernel (after the last iteration; otherwise folded
                                  into the next linearize_kernel)                           */
     TPLB_K_FINALIZE = 9,      /* finalize_kernel                                           */
-    TPLB_NUM_KERNEL_CLASSES = 10
+    TPLB_K_SOLO = 10,         /* solo_update_kernel: the whole update() in one launch      */
+    TPLB_NUM_KERNEL_CLASSES = 11
 };
 TPLB_API int32_t tplb_update_profiled(const tplb_batch* batch, void* stream,
                                       float* ms_by_class, int32_t* launches_by_class);

@@ -77,13 +77,21 @@ def _compile(src, out_so, flags):
     subprocess.run(cmd, check=True)
 
 
-def generate(name):
-    """Step 1: the reference's generator writes oracle/_ref/<name>/optim.c."""
+def reference_modules():
+    """The reference's own (genopt, symext, optimizers), unmodified."""
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
-    from tpl.optim import genopt, optimizers   # the reference, unmodified
+    from tpl.optim import genopt, optimizers, symext
+    return genopt, symext, optimizers
 
-    cfg = getattr(optimizers, "config_" + name)()
+
+def generate(name, cfg=None):
+    """Step 1: the reference's generator writes oracle/_ref/<name>/optim.c (`cfg`: a problem
+    definition made with the reference's own genopt.Config / symext; default: the zoo config)."""
+    genopt, _, optimizers = reference_modules()
+
+    if cfg is None:
+        cfg = getattr(optimizers, "config_" + name)()
     scratch = os.path.join(OUT, "_gen_" + name)
     shutil.rmtree(scratch, ignore_errors=True)
     cfg.output_dir = scratch
@@ -112,8 +120,8 @@ def generate(name):
     return code_hash
 
 
-def build(name, flavours=("fast", "strict")):
-    code_hash = generate(name)
+def build(name, flavours=("fast", "strict"), cfg=None):
+    code_hash = generate(name, cfg)
     dst = os.path.join(OUT, name)
     for fl in flavours:
         shutil.rmtree(os.path.join(dst, fl), ignore_errors=True)

@@ -3,6 +3,7 @@ construction defaults, setters, horizon clamp, deepcopy / __getstate__ — exerc
 on CPU buffers.  Compute entry points must refuse to run without CUDA."""
 
 import copy
+import os
 
 import numpy as np
 import pytest
@@ -146,3 +147,16 @@ def test_pipeline_needs_cuda(lateral):
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             SolverPipeline(lambda: lateral, depth=2)
+
+
+def test_generated_headers_are_current():
+    """The committed model headers are what the code generator emits today (a change to
+    codegen.py / derive.py / symext.py must be followed by `python -m tpl_b200.build --regen`)."""
+    from tpl_b200 import build, codegen, derive, optimizers
+    gen = build._generator_hash()
+    for name, make in optimizers.CONFIGS.items():
+        cfg = make()
+        text = codegen.emit_cuda_model(derive.derive(cfg), name, cfg.definition_hash())
+        first, rest = text.split("\n", 1)
+        with open(os.path.join(build.GENERATED, name + ".cuh")) as fd:
+            assert fd.read() == first + "\n// generator sha1: " + gen + "\n" + rest, name

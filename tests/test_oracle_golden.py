@@ -32,3 +32,31 @@ def test_golden_default_mode_flags():
     assert int(last["iterations"]) == 4 and int(last["termination_condition"]) == 2
     assert abs(last["traj_costs"] - 20.637620318244) < 1e-9
     assert abs(golden[0][0]["traj_costs"] - 195.177774308481) < 1e-9
+
+
+def test_port_matches_reference_extra_cases(oracle_libs, tmp_path):
+    """tests/extra.py: `ilr`, `shift`, `dynamics` / `ct_dynamics` (incl. the negative-index wrap),
+    sticky state, prev_x / prev_k, the two zoo models without a workload generator and a
+    user-defined RK4 + augmented-Lagrangian + end-cost problem — the C restatement against the
+    vectors recorded from the REAL reference (tests/golden/ref_extra.npz, make_golden_extra.py)."""
+    import os
+
+    import numpy as np
+
+    from tests import extra
+    from tpl_b200 import _cabi, build, genopt, symext as spx
+
+    want = dict(np.load(os.path.join(common.GOLDEN_DIR, "ref_extra.npz")))
+    name, lib = oracle_libs.build_custom(extra.custom_definition(genopt, spx), str(tmp_path))
+
+    def make(model):
+        if model == extra.CUSTOM:
+            return oracle_libs.OracleOptim(name, lib)
+        return oracle_libs.OracleOptim(model)
+
+    libs = build.build_zoo([n for n, _ in extra.ZOO])
+    zoo_info = {n: _cabi.model_info(_cabi.load(p)) for n, p in libs.items()}
+    got = extra.run_single(make, zoo_info)
+    assert set(got) == set(want)
+    worst, bad = extra.compare(got, want)
+    assert not bad, bad[:5]

@@ -34,6 +34,7 @@ class Batch(C.Structure):
         ("integrator_type", C.c_int32), ("use_quadratic_terms", C.c_int32),
         ("keep_previous", C.c_int32), ("precision", C.c_int32),
         ("line_search_rounds", C.c_int32), ("keep_records", C.c_int32),
+        ("single_launch", C.c_int32), ("reserved0", C.c_int32),
         ("dt", C.c_double), ("min_rel_cost_change", C.c_double),
         ("x", _D), ("u", _D), ("prev_x", _D), ("prev_k", _D), ("k", _D), ("K", _D), ("g", _D),
         ("lagrange_multiplier", _D), ("barrier_weight", _D), ("lg_mult_limit", _D),
@@ -45,6 +46,7 @@ class Batch(C.Structure):
         ("arrays", _D * MAX_ARRAYS), ("array_len", C.c_int32 * MAX_ARRAYS),
         ("workspace", _D), ("workspace_bytes", C.c_size_t),
         ("deriv_dense", _D),
+        ("horizons", _D),
     ]
 
 
@@ -113,7 +115,7 @@ def model_info(lib):
 
 
 KERNEL_CLASSES = ("stage_consts", "rollout_init", "multiplier", "linearize", "backward",
-                  "rollout", "stage_cost", "select", "accept", "finalize")
+                  "rollout", "stage_cost", "select", "accept", "finalize", "solo")
 
 
 def check(lib, code, what):

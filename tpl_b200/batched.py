@@ -209,7 +209,7 @@ class BatchedOptim:
                "trajectory_changed", "improved", "termination_condition")
     _SETTINGS = ("dt", "max_iterations", "max_lg_iterations", "min_rel_cost_change",
                  "opt_start", "use_quadratic_terms", "integrator_type", "keep_previous", "keep_records", "precision",
-                 "line_search_rounds")
+                 "line_search_rounds", "single_launch")
 
     def __init__(self, lib_path, batch=1, scenes=None, horizon_max=None, device=None):
         self._lib_path = lib_path
@@ -271,6 +271,7 @@ class BatchedOptim:
         self.keep_records = True           # fx..lux readable after update() (always true for small batches)
         self.precision = "fp64"            # "fp32": kernels compute in single precision
         self.line_search_rounds = 0        # 0 auto, 1 all step sizes at once, 2 in two rounds (tplb200.h)
+        self.single_launch = 0             # 0 auto, 1 whole update() in one launch (CTA per problem), -1 never
         self.params = BatchedParams(self)
 
     # -- settings -----------------------------------------------------------------
@@ -471,6 +472,7 @@ class BatchedOptim:
         q.keep_records = int(bool(self.keep_records))
         q.precision = {"fp64": 0, "fp32": 1}[self.precision]
         q.line_search_rounds = int(self.line_search_rounds)
+        q.single_launch = int(self.single_launch)
         q.dt = float(self.dt)
         q.min_rel_cost_change = float(self.min_rel_cost_change)
         for name, t in (("x", self._x), ("u", self._u), ("prev_x", self._prev_x), ("prev_k", self._prev_k),

@@ -50,12 +50,21 @@ def nvcc_path():
 
 def _solver_sources_hash():
     h = hashlib.sha1()
-    for fn in ("solver.cuh", "device_math.cuh", "fast_math.cuh", "cabi.cu"):
+    for fn in ("solver.cuh", "solo.cuh", "device_math.cuh", "fast_math.cuh", "cabi.cu"):
         with open(os.path.join(CSRC, fn), "rb") as fd:
             h.update(fd.read())
     with open(os.path.join(PKG, "..", "include", "tplb200.h"), "rb") as fd:
         h.update(fd.read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _generator_hash():
+    """sha1 over the sources that decide the text of a generated model header."""
+    h = hashlib.sha1()
+    for fn in ("codegen.py", "derive.py", "symext.py"):
+        with open(os.path.join(PKG, fn), "rb") as fd:
+            h.update(fd.read())
     return h.hexdigest()
 
 
@@ -85,14 +94,18 @@ def prepare_model_sources(config, name=None, lib_dir=None, regen=False) -> Prepa
     os.makedirs(os.path.dirname(header), exist_ok=True)
     os.makedirs(lib_dir, exist_ok=True)
 
+    # a header is reused only if both the problem definition and the code generator are unchanged
+    gen = _generator_hash()
     fresh = False
     if os.path.exists(header) and not regen:
         with open(header) as fd:
-            fresh = ("definition sha1: " + dh) in fd.read(400)
+            top = fd.read(400)
+            fresh = ("definition sha1: " + dh) in top and ("generator sha1: " + gen) in top
     if not fresh:
         text = codegen.emit_cuda_model(derive.derive(config), name, dh)
+        first, rest = text.split("\n", 1)
         with open(header, "w") as fd:
-            fd.write(text)
+            fd.write(first + "\n// generator sha1: " + gen + "\n" + rest)
     return Prepared(name, header, os.path.join(lib_dir, f"libtplb200_{name}.so"),
                     dh + ":" + _solver_sources_hash())
 

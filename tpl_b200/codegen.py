@@ -378,6 +378,11 @@ def derivative_layout(r):
     return slots, owner, n, offsets
 
 
+def _count_lookups(m):
+    names = {"lerp", "lerp_angle", "lerp_wrap", "box_interp", "blerp", "get_array_value"}
+    return len({f for e in _flatten(m) for f in sp.sympify(e).atoms(sp.Function) if type(f).__name__ in names})
+
+
 def emit_cuda_model(d: Derivation, name: str, definition_hash: str) -> str:
     """The ``struct Model`` consumed by csrc/solver.cuh."""
     r, hoisted = hoist_stage_constants(d)
@@ -437,6 +442,8 @@ def emit_cuda_model(d: Derivation, name: str, definition_hash: str) -> str:
         + "\n    // per-(scene, stage) constants: lookups that depend on the stage index only\n"
         + hoisted_doc
         + f"    static constexpr int NUM_STAGE_CONSTS = {len(hoisted)};\n"
+        + "    // array lookups left in the dynamics (their argument depends on the state): such a rollout branches\n"
+        + f"    static constexpr int DYNAMICS_LOOKUPS = {_count_lookups(r['ctDynamics'])};\n"
         + "\n    // one stage's derivative record: dense order fx|fu|lx|lu|lxx|luu|lux (row-major);\n"
         + "    // deriv_slot(e) >= 0: index in the compact record, -1: identically 0, -2: identically 1\n"
         + f"    static constexpr int DERIV_DENSE = {len(slots)};\n"

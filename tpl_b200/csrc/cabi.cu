@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "solver.cuh"
+#include "solo.cuh"
 
 // Internal linkage: several solver libraries (one per problem definition) are loaded
 // into the same process, and their `Model` types must not be merged by the dynamic
@@ -54,6 +55,8 @@ int validate(const tplb_batch* q) {
         return fail(TPLB_E_UNSUPPORTED, "precision must be TPLB_FP64 or TPLB_FP32");
     if (q->line_search_rounds < 0 || q->line_search_rounds > 2)
         return fail(TPLB_E_ARG, "line_search_rounds must be 0, 1 or 2");
+    if (q->single_launch < -1 || q->single_launch > 1 || q->reserved0 != 0)
+        return fail(TPLB_E_ARG, "single_launch must be -1, 0 or 1");
     if (!q->x || !q->u || !q->k || !q->K || !q->u_min || !q->u_max || !q->traj_costs || !q->alpha ||
         !q->mu || !q->iterations || !q->lg_iterations || !q->mu_step || !q->trajectory_changed ||
         !q->improved || !q->termination_condition || !q->scene_index || !q->workspace)
@@ -197,8 +200,65 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof);
 
 // precision 0: every kernel computes in fp64; 1: the kernels compute in fp32 (storage, cost
 // sums and all accept / stop decisions stay fp64)
+// ---- one launch, one thread block per problem (solo.cuh) --------------------------------------
+size_t solo_smem_limit() {
+    static int limit = -1;                                 // of the first device used; B200 boxes are uniform
+    if (limit < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) limit = 0;
+    }
+    return (size_t)limit;
+}
+
+size_t solo_smem_bytes(const tplb_batch& q) {
+    int samples = 0;
+    for (int a = 0; a < Model::NUM_ARRAYS; ++a) samples += q.array_len[a];
+    return tplb::SoloLayout<Model>::bytes(q.horizon, samples);
+}
+
+bool solo_eligible(const tplb_batch& q) {
+    return q.precision == TPLB_FP64 && q.use_quadratic_terms && solo_smem_bytes(q) <= solo_smem_limit();
+}
+
+// automatic choice: as long as every problem gets its own SM (measured crossover on B200)
+int solo_auto_batch() {
+    static const int n = [] {
+        const char* e = std::getenv("TPLB_SOLO_MAX_BATCH");
+        return e ? std::atoi(e) : 296;
+    }();
+    return n;
+}
+
+int run_solo(const tplb_batch& q, cudaStream_t st, Profiler& prof) {
+    const tplb::Workspace ws = tplb::carve<Model>(q.workspace, q.batch, q.scenes, q.t_max);
+    const size_t smem = solo_smem_bytes(q);
+    prof.before();
+#define TPLB_SOLO(SCHEME)                                                                             \
+    do {                                                                                              \
+        auto kern = tplb::solo_update_kernel<Model, SCHEME>;                                          \
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+        kern<<<q.batch, tplb::kSoloThreads, smem, st>>>(q, ws);                                       \
+    } while (0)
+    switch (q.integrator_type) {
+        case TPLB_EULER: TPLB_SOLO(TPLB_EULER); break;
+        case TPLB_HEUN: TPLB_SOLO(TPLB_HEUN); break;
+        default: TPLB_SOLO(TPLB_RK4); break;
+    }
+#undef TPLB_SOLO
+    prof.after(TPLB_K_SOLO);
+    return check_launch("tplb_update (single launch)");
+}
+
 int run_update(const tplb_batch* qp, void* stream_, Profiler& prof) {
     if (int e = validate(qp)) return e;
+    const bool solo = qp->single_launch > 0 || (qp->single_launch == 0 && qp->batch <= solo_auto_batch() && solo_eligible(*qp));
+    if (solo) {
+        if (!solo_eligible(*qp))
+            return fail(TPLB_E_UNSUPPORTED, "single_launch needs fp64, use_quadratic_terms and a problem that fits shared memory");
+        return run_solo(*qp, static_cast<cudaStream_t>(stream_), prof);
+    }
+    if (qp->horizons) return fail(TPLB_E_UNSUPPORTED, "per-problem horizons need the single-launch path");
     return qp->precision == TPLB_FP32 ? run_update_as<float>(qp, stream_, prof)
                                       : run_update_as<double>(qp, stream_, prof);
 }
@@ -385,6 +445,17 @@ int32_t tplb_selftest_math(int32_t fn, const double* x, int32_t n, double* out, 
     tplb::math_selftest_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream_)>>>(fn, x, n, out);
     return check_launch("tplb_selftest_math");
 }
+
+#ifdef TPLB_SOLO_TIMING
+// development aid: cycles per phase of solo_update_kernel (block 0), accumulated since the last call
+__attribute__((visibility("default"))) int32_t tplb_debug_solo_cycles(long long* out) {
+    long long zero[8] = {0};
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, tplb::g_solo_cycles, sizeof zero);
+    cudaMemcpyToSymbol(tplb::g_solo_cycles, zero, sizeof zero);
+    return 0;
+}
+#endif
 
 double tplb_measure_fp64_tflops(int32_t repeats, void* stream_) {
     cudaStream_t st = static_cast<cudaStream_t>(stream_);

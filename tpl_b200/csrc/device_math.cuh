@@ -56,12 +56,72 @@ __device__ __forceinline__ int sample_index(R v, int n) {
     return static_cast<int>(v);
 }
 
+// fmod(a, b) for b > 0: |a| < b returns a itself (what fmod returns, exactly); libdevice's general
+// algorithm (a loop of scaled subtractions) runs only for the rare larger arguments
+template <typename R>
+__device__ __forceinline__ R fmod_small(R a, R b) {
+    return (fabs(a) < b) ? a : fmod(a, b);
+}
+
 // optim.c:332-338
 template <typename R>
 __device__ __forceinline__ R short_angle_dist(R from, R to) {
     const R turn = R(3.14159265358979323846) * 2;
-    const R d = fmod(to - from, turn);
-    return fmod(2 * d, turn) - d;
+    const R d = fmod_small(to - from, turn);
+    return fmod_small(2 * d, turn) - d;
+}
+
+// ---------------------------------------------------------------------------------
+// the reference's lookups on one row of samples (optim.c:330-406).  kGlobal: the row is in
+// global memory and read through the read-only path; otherwise it was staged in shared memory.
+// ---------------------------------------------------------------------------------
+template <typename R, bool kGlobal>
+__device__ __forceinline__ R sample_at(const double* p) {
+    if constexpr (kGlobal) return R(__ldg(p));
+    else return R(*p);
+}
+
+// optim.c:374-388 (+ initInterp :347-355)
+template <typename R, bool kGlobal>
+__device__ __forceinline__ R row_lerp(const double* p, int n, R x0, R dx, R x) {
+    if (n == 0) return R(0);
+    const R q = (x - x0) / dx;
+    const int lo = sample_index(floor(q), n);
+    const int hi = sample_index(ceil(q), n);
+    R w = q - R(lo);
+    w = (R(0) > w) ? R(0) : w;
+    w = (w < R(1)) ? w : R(1);
+    return (R(1) - w) * sample_at<R, kGlobal>(p + lo) + w * sample_at<R, kGlobal>(p + hi);
+}
+
+// optim.c:392-406
+template <typename R, bool kGlobal>
+__device__ __forceinline__ R row_lerp_angle(const double* p, int n, R x0, R dx, R x) {
+    if (n == 0) return R(0);
+    const R q = (x - x0) / dx;
+    const int lo = sample_index(floor(q), n);
+    const int hi = sample_index(ceil(q), n);
+    R w = q - R(lo);
+    w = (R(0) > w) ? R(0) : w;
+    w = (w < R(1)) ? w : R(1);
+    const R v0 = sample_at<R, kGlobal>(p + lo);
+    return v0 + short_angle_dist(v0, sample_at<R, kGlobal>(p + hi)) * w;
+}
+
+// optim.c:357-370
+template <typename R, bool kGlobal>
+__device__ __forceinline__ R row_box_interp(const double* p, int n, R dx, R x) {
+    if (n == 0) return R(0);
+    return sample_at<R, kGlobal>(p + sample_index(floor(x / dx), n));
+}
+
+// optim.c:330 — the reference indexes unchecked; clamp instead of reading out of bounds
+template <typename R, bool kGlobal>
+__device__ __forceinline__ R row_value(const double* p, int n, R i) {
+    if (n == 0) return R(0);
+    int j = static_cast<int>(i);
+    j = j < 0 ? 0 : (j >= n ? n - 1 : j);
+    return sample_at<R, kGlobal>(p + j);
 }
 
 // Parameter view of ONE problem: scalars of its scene and its scene's rows of the
@@ -81,51 +141,12 @@ struct ParamView {
     __device__ __forceinline__ const double* row(int a) const {
         return arrays[a] + (size_t)scene * len[a];
     }
-
-    // optim.c:374-388 (+ initInterp :347-355)
-    __device__ __forceinline__ R lerp(int a, R x0, R dx, R x) const {
-        const int n = len[a];
-        if (n == 0) return R(0);
-        const R q = (x - x0) / dx;
-        const int lo = sample_index(floor(q), n);
-        const int hi = sample_index(ceil(q), n);
-        R w = q - R(lo);
-        w = (R(0) > w) ? R(0) : w;
-        w = (w < R(1)) ? w : R(1);
-        const double* p = row(a);
-        return (R(1) - w) * R(__ldg(p + lo)) + w * R(__ldg(p + hi));
-    }
-
-    // optim.c:392-406
+    __device__ __forceinline__ R lerp(int a, R x0, R dx, R x) const { return row_lerp<R, true>(row(a), len[a], x0, dx, x); }
     __device__ __forceinline__ R lerp_angle(int a, R x0, R dx, R x) const {
-        const int n = len[a];
-        if (n == 0) return R(0);
-        const R q = (x - x0) / dx;
-        const int lo = sample_index(floor(q), n);
-        const int hi = sample_index(ceil(q), n);
-        R w = q - R(lo);
-        w = (R(0) > w) ? R(0) : w;
-        w = (w < R(1)) ? w : R(1);
-        const double* p = row(a);
-        const R v0 = R(__ldg(p + lo));
-        return v0 + short_angle_dist(v0, R(__ldg(p + hi))) * w;
+        return row_lerp_angle<R, true>(row(a), len[a], x0, dx, x);
     }
-
-    // optim.c:357-370
-    __device__ __forceinline__ R box_interp(int a, R dx, R x) const {
-        const int n = len[a];
-        if (n == 0) return R(0);
-        return R(__ldg(row(a) + sample_index(floor(x / dx), n)));
-    }
-
-    // optim.c:330 — the reference indexes unchecked; clamp instead of reading out of bounds
-    __device__ __forceinline__ R array_value(int a, R i) const {
-        const int n = len[a];
-        if (n == 0) return R(0);
-        int j = static_cast<int>(i);
-        j = j < 0 ? 0 : (j >= n ? n - 1 : j);
-        return R(__ldg(row(a) + j));
-    }
+    __device__ __forceinline__ R box_interp(int a, R dx, R x) const { return row_box_interp<R, true>(row(a), len[a], dx, x); }
+    __device__ __forceinline__ R array_value(int a, R i) const { return row_value<R, true>(row(a), len[a], i); }
 };
 
 
@@ -143,6 +164,25 @@ struct CachedParamView : ParamView<R> {
         for (int i = 0; i < NS; ++i) cached[i] = base.scalar(i);
     }
     __device__ __forceinline__ R scalar(int i) const { return cached[i]; }
+};
+
+// Parameters of ONE problem held on chip: scalars in registers, the rows of its parameter arrays
+// (reference path / map samples) staged in shared memory — the one-launch kernel (solo.cuh) looks
+// them up inside its serial rollout chain, where a global-memory round trip per lookup would
+// dominate the stage.
+template <typename R, int NS, int NA>
+struct StagedParamView {
+    R cached[NS > 0 ? NS : 1];
+    const double* rows[NA > 0 ? NA : 1];          // shared memory
+    int32_t len[NA > 0 ? NA : 1];
+
+    __device__ __forceinline__ R scalar(int i) const { return cached[i]; }
+    __device__ __forceinline__ R lerp(int a, R x0, R dx, R x) const { return row_lerp<R, false>(rows[a], len[a], x0, dx, x); }
+    __device__ __forceinline__ R lerp_angle(int a, R x0, R dx, R x) const {
+        return row_lerp_angle<R, false>(rows[a], len[a], x0, dx, x);
+    }
+    __device__ __forceinline__ R box_interp(int a, R dx, R x) const { return row_box_interp<R, false>(rows[a], len[a], dx, x); }
+    __device__ __forceinline__ R array_value(int a, R i) const { return row_value<R, false>(rows[a], len[a], i); }
 };
 
 }  // namespace tplb

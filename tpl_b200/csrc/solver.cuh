@@ -98,6 +98,8 @@ struct Workspace {
     int32_t* pending;      // [B]  problems whose round-1 step sizes all failed (unordered list)
     int32_t* pending_count;// [1]
     int32_t* records_f32;  // [1]  1: the derivative records were written as fp32
+    int32_t* last_tried;   // [B]  candidate the last line search of the problem ended on (the reference's
+                           //      next_x / next_u): the accepted one, or alpha = 1e-7 after a failed search; -1: none yet
     int32_t* lam_zero;     // [B]  1: every multiplier limit of the problem is 0, so after the
                            //      multiplier update lambda is identically 0 (pure penalty — the setting of
                            //      all shipped callers) and need not be read
@@ -125,6 +127,7 @@ __host__ __device__ inline Workspace carve(void* base, int B, int S, int t_max, 
     w.pending_count = reinterpret_cast<int32_t*>(take(sizeof(int32_t)));
     w.records_f32 = reinterpret_cast<int32_t*>(take(sizeof(int32_t)));
     w.lam_zero = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)B));
+    w.last_tried = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * (size_t)B));
     if (total) *total = off;
     return w;
 }
@@ -714,39 +717,54 @@ __global__ void expand_derivatives_kernel(const __grid_constant__ tplb_batch q, 
 // ---------------------------------------------------------------------------------
 // gains  k = -(Quu + mu I)^-1 Qu,  K = -(Quu + mu I)^-1 Qux   (optim.c:243-291)
 // ---------------------------------------------------------------------------------
-template <int X, int U, typename R>
-__device__ __forceinline__ void control_gains(const R (&Quu)[U][U], const R (&Qu)[U],
-                                              const R (&Qux)[U][X], R mu,
-                                              R (&k)[U], R (&K)[U][X]) {
+// -(Quu + mu I)^-1 for one or two controls (optim.c:243-291): U == 1 tests the un-regularised
+// value and returns 0 gains otherwise; U == 2 is the closed-form inverse without a definiteness check
+template <int U, typename R>
+__device__ __forceinline__ void gain_inverse(const R (&Quu)[U][U], R mu, R (&Mi)[U][U]) {
     static_assert(U == 1 || U == 2, "more than two controls are not supported (genopt.py:420-425)");
     if constexpr (U == 1) {
         R s = R(0);
         if (Quu[0][0] > R(0)) s = R(-1) / (Quu[0][0] + mu);     // test on the un-regularised value
-        k[0] = Qu[0] * s;
-#pragma unroll
-        for (int j = 0; j < X; ++j) K[0][j] = Qux[0][j] * s;
+        Mi[0][0] = s;
     } else {
         const R a = Quu[0][0] + mu, bb = Quu[0][1], d = Quu[1][1] + mu;
         const R det = a * d - bb * bb;
         const R s = R(-1) / det;                          // no definiteness check
-        R Mi[2][2];
         Mi[0][0] = d * s;
         Mi[0][1] = -bb * s;
         Mi[1][0] = Mi[0][1];
         Mi[1][1] = a * s;
+    }
+}
+
+// one row of  Mi * v  as the reference's matrix product forms it
+template <int U, typename R>
+__device__ __forceinline__ R gain_row(const R (&Mi)[U][U], int i, const R (&v)[U]) {
+    if constexpr (U == 1) {
+        return v[0] * Mi[0][0];
+    } else {
+        R acc = R(0);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            R acc = R(0);
+        for (int c = 0; c < 2; ++c) acc += Mi[i][c] * v[c];
+        return acc;
+    }
+}
+
+template <int X, int U, typename R>
+__device__ __forceinline__ void control_gains(const R (&Quu)[U][U], const R (&Qu)[U],
+                                              const R (&Qux)[U][X], R mu,
+                                              R (&k)[U], R (&K)[U][X]) {
+    R Mi[U][U];
+    gain_inverse<U, R>(Quu, mu, Mi);
 #pragma unroll
-            for (int c = 0; c < 2; ++c) acc += Mi[i][c] * Qu[c];
-            k[i] = acc;
+    for (int i = 0; i < U; ++i) {
+        k[i] = gain_row<U, R>(Mi, i, Qu);
 #pragma unroll
-            for (int j = 0; j < X; ++j) {
-                R r = R(0);
+        for (int j = 0; j < X; ++j) {
+            R col[U];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) r += Mi[i][c] * Qux[c][j];
-                K[i][j] = r;
-            }
+            for (int c = 0; c < U; ++c) col[c] = Qux[c][j];
+            K[i][j] = gain_row<U, R>(Mi, i, col);
         }
     }
 }
@@ -1232,38 +1250,63 @@ __global__ void backward_first_order_kernel(const __grid_constant__ tplb_batch q
 // the reference selects (optim.c:861-869).  Then the regularisation schedule and the
 // relative-change stop test (optim.c:987-1006).
 // ---------------------------------------------------------------------------------
-// everything the reference does once the search has ended for a problem (optim.c:849-851, 987-1006)
-__device__ __forceinline__ void conclude_line_search(const tplb_batch& q, const Workspace& ws, int b,
-                                                     int win, double before, double now) {
-    const int B = q.batch;
-    ws.winner[b] = win;
-    ws.counters[(size_t)2 * B + b] += (win >= 0) ? win + 1 : kAlphas;   // rollouts a sequential search runs
+// everything the reference does once the search has ended for a problem (optim.c:849-851, 987-1006);
+// the status words are handed in by reference: global arrays (batched kernels) or shared memory
+// (one-launch kernel, solo.cuh)
+struct SearchStatus {
+    double& traj_costs;
+    double& alpha;
+    double& mu;
+    int32_t& mu_step;
+    int32_t& trajectory_changed;
+    int32_t& improved;
+    int32_t& termination_condition;
+    int32_t& running;
+    int32_t& winner;
+    int32_t& last_tried;        // candidate the reference's next_x / next_u hold after this search
+    int32_t& rollouts;          // rollouts a sequential search runs
+};
+
+__device__ __forceinline__ void conclude_core(const SearchStatus& s, bool second_order, double min_rel_cost_change,
+                                              int win, double before, double now) {
+    s.winner = win;
+    s.last_tried = win >= 0 ? win : kAlphas - 1;
+    s.rollouts += (win >= 0) ? win + 1 : kAlphas;
     {
         double tn = 1.0;                                     // alpha of the last step tried (optim.c:863)
         for (int i = 0; i < (win < 0 ? kAlphas - 1 : win); ++i) tn *= 10.0;
-        q.alpha[b] = 1.0 / tn;
+        s.alpha = 1.0 / tn;
     }
     if (win >= 0) {
-        q.traj_costs[b] = now;
-        q.trajectory_changed[b] = 1;
-        q.improved[b] = 1;
+        s.traj_costs = now;
+        s.trajectory_changed = 1;
+        s.improved = 1;
     }
-    if (q.use_quadratic_terms) {                             // regularisation schedule (optim.c:989-999)
-        int ms = q.mu_step[b];
+    if (second_order) {                                      // regularisation schedule (optim.c:989-999)
+        int ms = s.mu_step;
         ms = (win >= 0) ? (ms - 1 > 0 ? ms - 1 : 0) : (ms + 1 < 7 ? ms + 1 : 7);
-        q.mu_step[b] = ms;
+        s.mu_step = ms;
         double m = 0.0;
         if (ms > 0) {
             m = 1.0;
             for (int i = 1; i < ms; ++i) m *= 10.0;          // 10^(ms-1), exact
         }
-        q.mu[b] = m;
+        s.mu = m;
     }
     const double rel = fabs(now - before) / now;             // optim.c:1001-1006
-    if (rel < q.min_rel_cost_change) {
-        q.termination_condition[b] = 2;
-        ws.running[b] = 0;
+    if (rel < min_rel_cost_change) {
+        s.termination_condition = 2;
+        s.running = 0;
     }
+}
+
+__device__ __forceinline__ void conclude_line_search(const tplb_batch& q, const Workspace& ws, int b,
+                                                     int win, double before, double now) {
+    const int B = q.batch;
+    const SearchStatus s{q.traj_costs[b], q.alpha[b], q.mu[b], q.mu_step[b], q.trajectory_changed[b],
+                         q.improved[b], q.termination_condition[b], ws.running[b], ws.winner[b],
+                         ws.last_tried[b], ws.counters[(size_t)2 * B + b]};
+    conclude_core(s, q.use_quadratic_terms != 0, q.min_rel_cost_change, win, before, now);
 }
 
 // cost of candidate a of problem b: the stage terms added in the reference's order
