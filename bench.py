@@ -43,7 +43,36 @@ FLOPS = {
     # fwd = feedback (X+2U+2UX = 34) + HEUN (2 F_ct + 5X = 70) + stage cost (84 + 4 lookups x 9 + 1 = 121)
     "trajectory_tracking_mpc_time": dict(lin=366, bwd=1717, fwd=225, fwd_chain=104, fwd_cost=121, con=9,
                                          sp_lin=22, sp_fwd=12),
+    # F_lin = 268 (+11 special), F_bwd = 118, F_fwd (EULER) = 89, constraints 5 + 2 lookups
+    "lateral_profile": dict(lin=268, bwd=118, fwd=89, con=23, sp_lin=11, sp_fwd=0),
 }
+
+
+def algorithmic_flops(opt, model, T, max_lg):
+    """F_solve summed over the batch from the work the reference would have done (work counters)."""
+    F = FLOPS[model]
+    lin, bwd, roll = (int(c.sum().item()) for c in opt.work_counters())
+    return (lin * F["lin"] + bwd * F["bwd"] + roll * F["fwd"] + opt.batch * F["con"] * max_lg) * T
+
+
+def algorithmic_bytes(opt, T, iterations, pure_penalty, fp32=False):
+    """HBM bytes the throughput sequence has to move per batch: sweep (accepted candidate, box limits
+    [, multipliers] in; x, u, K, k out) + rollouts (u, k, limits, K, x [, multipliers] in; two
+    candidates out) per stage and iteration.  fp32 mode stores the candidates in 4 bytes."""
+    X, U, C = opt.X, opt.U, opt.C
+    lam = 0 if pure_penalty else C
+    cand = 4 if fp32 else 8
+    sweep = (X + U) * cand + (2 * U + lam + (X + U) + U * X + U) * 8
+    roll = (4 * U + U * X + X + lam) * 8 + 2 * (X + U) * cand
+    return (sweep + roll) * T * iterations * opt.batch
+
+
+def hbm_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fd:
+            return json.load(fd)["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (copy bandwidth, burst)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
 
 
 def parse():
@@ -368,6 +397,13 @@ def run_ours(a):
                          f"{e2e_cost_check!r} vs {resident_cost_check!r}")
     e2e_value = world * B * a.steps / (e2e_ms * 1e-3)
 
+    # ---- BASELINE.json configs[2]: every rank takes part (scene-sharded, one final gather) -----
+    peak_fp64 = opt.measure_fp64_tflops()
+    cfg3 = None
+    if not a.skip_configs:
+        pipe.synchronize()
+        cfg3 = config3_multistart(a, world, rank, dev, peak_fp64)
+
     # ---- attribution: time per kernel class and algorithmic work (rank 0) ----------------
     line = None
     if rank == 0:
@@ -523,10 +559,13 @@ def run_ours(a):
             # second half of the metric: p50 latency of ONE solve (batch = 1), same problem shape
             line["latency"] = single_solve_latency(lib, pb, cpu=True)
             if not a.skip_configs:
-                line["configs"] = other_configs(a)
+                line["configs"] = {"3_multistart_65536": cfg3, "4_lateral_16384": config4_lateral(a, peak_fp64),
+                                   "5_mpc_dead_time_32768": config5_mpc_dead_time(a, peak_fp64)}
             # row f2: the profile shaping that precedes the lateral / velocity solves
             line["profile_shaping"] = profile_shaping()
     if world > 1:
+        if line is not None and cfg3 is not None:
+            line["configs"] = {"3_multistart_65536": cfg3}
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
@@ -591,8 +630,288 @@ def parity_against(solved, bases, mirror, pb, lib, rtol=1e-9):
                        "level, verified iteration by iteration (agreement within rtol up to the flip)"}
 
 
-def other_configs(a):
-    return {}
+def graph_pipeline(make_solver, depth, body):
+    """`depth` solvers on their own streams, `body(slot)` captured once per slot as a CUDA graph."""
+    from tpl_b200.streaming import SolverPipeline
+    pipe = SolverPipeline(make_solver, depth=depth)
+    for slot in pipe.slots:
+        slot.capture(body)
+    return pipe
+
+
+def time_pipeline(pipe, steps, warmup, after=None):
+    """CUDA-event time of `steps` replays (round-robin over the slots) after `warmup` replays."""
+    import torch
+    for _ in range(max(warmup, len(pipe)) if warmup else 0):
+        pipe.next().replay()
+    pipe.join()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pipe.fork()
+    for _ in range(steps):
+        pipe.next().replay()
+    if after is not None:
+        after()
+    pipe.join()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def cpu_sample(pb, n, cores, what):
+    v, kind, used = cpu_throughput(pb, n, cores, repeats=2)
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"first {used} problems of {what}, one Optim object per problem, {cores} threads, "
+                      "update() only, best of 2"}
+
+
+def config3_multistart(a, world, rank, dev, peak_fp64):
+    """BASELINE.json configs[2]: 65536 = 64 scenes x 1024 multi-start problems of the headline model,
+    sharded BY SCENE over the ranks (every argmin group stays on one GPU, the scene's reference
+    arrays live only on the rank that owns it), no collective inside the solves and ONE gather of
+    (min cost, argmin) per scene after the last step.  Strong scaling: the 65536 problems are
+    fixed, every rank solves its scenes in up to 4 sub-batches in flight."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tpl_b200 import build, dist as tdist, scenarios as sc
+    from tpl_b200.batched import BatchedOptim
+    scenes, per, T, I = 64, 1024, a.horizon, a.iterations
+    lib = build.zoo_library_path(MODEL)
+    (s_lo, s_hi), (p_lo, p_hi) = tdist.shard_scenes(scenes, per, rank, world)
+    counts = [hi - lo for lo, hi in (tdist.shard_range(scenes, r, world) for r in range(world))]
+    mine = s_hi - s_lo
+    depth = max(1, min(4, mine))
+    bounds = [tdist.shard_range(mine, i, depth) for i in range(depth)]          # scenes of each sub-batch
+    subs = [sc.mpc_time(batch=(hi - lo) * per, scenes=hi - lo, horizon=T, max_iterations=I, forced=True,
+                        seed0=s_lo + lo) for lo, hi in bounds]
+    it = iter(subs)
+
+    def make():
+        pb = next(it)
+        o = sc.apply_to_batched(BatchedOptim(lib, batch=pb.batch, scenes=pb.scenes, horizon_max=T), pb)
+        o.line_search_rounds, o.keep_previous, o.keep_records = 2, False, False
+        o.single_launch = -1
+        o._fresh = (o._x[0].clone(), o._u.clone())
+        return o
+
+    def body(slot):
+        o = slot.opt
+        o._x[0].copy_(o._fresh[0]); o._u.copy_(o._fresh[1])
+        o.lagrange_multiplier = 0.0; o.mu = 0.0; o.mu_step = 0
+        o.update()
+
+    pipe = graph_pipeline(make, depth, body)
+    result = {}
+
+    def gather():
+        mins, args = [], []
+        for slot, (lo, hi) in zip(pipe.slots, bounds):
+            with slot:
+                mn, am = slot.opt.argmin_groups(per)
+            torch.cuda.current_stream().wait_stream(slot.stream)
+            mins.append(mn); args.append(am.to(torch.int64) + lo * per)
+        result["best"] = tdist.gather_best(torch.cat(mins), torch.cat(args).to(torch.int32), p_lo, counts=counts)
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # (1) ONE pass over the 65536 problems from idle, gather included: what a planner waits for
+    one_pass = []
+    for _ in range(3):
+        if world > 1:
+            dist.barrier()
+        one_pass.append(max_over_ranks(time_pipeline(pipe, depth, 0, after=gather)))
+    # (2) steady state: `passes` passes back to back (fill / drain of the streams amortised)
+    passes = 6
+    steps = passes * depth
+    if world > 1:
+        dist.barrier()
+    ms = max_over_ranks(time_pipeline(pipe, steps, 1, after=gather))
+    gmin, garg = result["best"]
+    value = scenes * per * passes / (ms * 1e-3)
+    out = {"workload": f"65536 = {scenes} scenes x {per} multi-start {MODEL} problems, N={T}, {I} forced iterations, "
+                       f"fp64, sharded by scene over {world} GPU(s), parameters per scene on the owning rank",
+           "value": value, "unit": UNIT, "n_gpus": world, "scaling": "strong", "ms_per_pass": ms / passes,
+           "single_pass_ms": min(one_pass), "single_pass_solves_per_s": scenes * per / (min(one_pass) * 1e-3),
+           "sub_batches_in_flight_per_gpu": depth,
+           "collective": "one all_gather of (min cost, argmin) per scene after the last step" if world > 1 else "none",
+           "best_cost_checksum": float(gmin.sum()), "argmin_checksum": int(garg.sum())}
+    lin, bwd, roll = (float(c.double().mean()) for c in pipe.slots[0].opt.work_counters())
+    out["work_per_solve"] = {"linearisations": lin, "backward_sweeps": bwd, "rollouts": roll}
+    # agreement with a single-GPU solve: rank 0 re-solves the first scene of every other rank itself
+    if world > 1 and rank == 0:
+        firsts = [tdist.shard_range(scenes, r, world)[0] for r in range(1, world)]
+        ok, worst = True, 0.0
+        for s0 in firsts:
+            pb = sc.mpc_time(batch=per, scenes=1, horizon=T, max_iterations=I, forced=True, seed0=s0)
+            o = sc.apply_to_batched(BatchedOptim(lib, batch=per, scenes=1, horizon_max=T), pb)
+            o.single_launch = -1
+            o.update()
+            mn, am = o.argmin_groups(per)
+            worst = max(worst, abs(float(mn[0]) - float(gmin[s0])) / abs(float(gmin[s0])))
+            ok = ok and int(am[0]) + s0 * per == int(garg[s0])
+        out["argmin_agreement"] = {"scenes_rechecked_on_rank0": len(firsts), "argmin_equal": ok,
+                                   "worst_rel_cost": worst}
+        if not ok or worst > 1e-12:
+            raise SystemExit(f"config #3: sharded argmin differs from a single-GPU solve ({out['argmin_agreement']})")
+    if rank == 0:
+        o = pipe.slots[0].opt
+        fl = algorithmic_flops(o, MODEL, T, 1) / o.batch * scenes * per * passes
+        by = algorithmic_bytes(o, T, I, True) / o.batch * scenes * per * passes
+        hbm, src = hbm_peak_gbs()
+        out["roofline"] = {"fp64": {"achieved": fl / (ms * 1e-3) / 1e12, "peak": peak_fp64, "unit": "TFLOP/s",
+                                    "frac": fl / (ms * 1e-3) / 1e12 / (peak_fp64 * world)},
+                           "hbm": {"achieved": by / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                   "frac": by / (ms * 1e-3) / 1e9 / (hbm * world), "peak_source": src},
+                           "note": "whole step, all GPUs: algorithmic flops / bytes over the measured time, "
+                                   "fractions against n_gpus x the single-GPU peak"}
+        if world == 1:
+            out["cpu_baseline"] = cpu_sample(subs[0], 512, os.cpu_count() or 1, "the first scene's starts")
+    del pipe
+    torch.cuda.empty_cache()
+    return out if rank == 0 else None
+
+
+def config4_lateral(a, peak_fp64):
+    """BASELINE.json configs[3]: lateral profile with corridor constraints (acc_2024 weights), N=200,
+    batch 16384 — the shipped pure-penalty setting and the augmented-Lagrangian variant
+    (lg_mult_limit 0.1, 3 outer iterations), 10 forced iterations, 4 batches in flight."""
+    import torch
+    from tpl_b200 import build, scenarios as sc
+    from tpl_b200.batched import BatchedOptim
+    B, T, I, depth = 16384, 200, 10, 4
+    lib = build.zoo_library_path("lateral_profile")
+    out = {}
+    hbm, src = hbm_peak_gbs()
+    for key, al in (("penalty", False), ("augmented_lagrangian", True)):
+        pb = sc.lateral(batch=B, horizon=T, max_iterations=I, forced=True, augmented_lagrangian=al)
+
+        def make():
+            o = sc.apply_to_batched(BatchedOptim(lib, batch=B, horizon_max=T), pb)
+            o.line_search_rounds, o.keep_previous, o.keep_records = 2, False, False
+            o._fresh = (o._x[0].clone(), o._u.clone())
+            return o
+
+        def body(slot):
+            o = slot.opt
+            o._x[0].copy_(o._fresh[0]); o._u.copy_(o._fresh[1])
+            o.lagrange_multiplier = 0.0; o.mu = 0.0; o.mu_step = 0
+            o.update()
+
+        pipe = graph_pipeline(make, depth, body)
+        steps = 6 * depth
+        ms = time_pipeline(pipe, steps, 1)
+        o = pipe.slots[0].opt
+        fl = algorithmic_flops(o, "lateral_profile", T, pb.max_lg_iterations) * steps
+        by = algorithmic_bytes(o, T, I * pb.max_lg_iterations, not al) * steps
+        out[key] = {"workload": f"{B} lateral_profile problems (X=2,U=1,C=2), N={T}, {I} forced iterations x "
+                                f"{pb.max_lg_iterations} outer iteration(s), EULER, fp64, barrier_weight 1000, "
+                                f"lg_mult_limit {pb.lg_mult_limit}, {depth} batches in flight",
+                    "value": B * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+                    "roofline": {"fp64": {"achieved": fl / (ms * 1e-3) / 1e12, "peak": peak_fp64, "unit": "TFLOP/s",
+                                          "frac": fl / (ms * 1e-3) / 1e12 / peak_fp64},
+                                 "hbm": {"achieved": by / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                         "frac": by / (ms * 1e-3) / 1e9 / hbm, "peak_source": src}},
+                    "cpu_baseline": cpu_sample(pb, 512, os.cpu_count() or 1, "the same batch")}
+        del pipe
+        torch.cuda.empty_cache()
+    return out
+
+
+def config5_mpc_dead_time(a, peak_fp64):
+    """BASELINE.json configs[4]: the MPC with dead-time compensation over 32768 perturbed scenarios.
+    One step = the 18 batched `dynamics()` calls of 0.01 s that roll the measured state forward over
+    the actuator dead time with the recorded steering / acceleration history
+    (control/model_predictive_controller_time.py:159-171), then the solve with ref_t_offset = 0.18
+    (N=40, the shipped horizon; 20 iterations, default stop rule) — in the optional fp32 compute
+    mode and in fp64, both checked against the reference's fp64 solver doing the same."""
+    import numpy as np
+    import torch
+    from tpl_b200 import build, scenarios as sc
+    from tpl_b200.batched import BatchedOptim
+    B, T, I, steps_dt, cycle, depth = 32768, 40, 20, 18, 0.01, 4
+    lib = build.zoo_library_path(MODEL)
+    pb = sc.mpc_time(batch=B, horizon=T, max_iterations=I, forced=False, seed0=9000)
+    pb.scalars["ref_t_offset"][:] = steps_dt * cycle
+    rng = np.random.default_rng(5)
+    hist = np.stack([rng.uniform(-0.05, 0.05, (steps_dt, B)), rng.uniform(-1.0, 1.0, (steps_dt, B))])   # delta, acc
+    out = {}
+    hbm, src = hbm_peak_gbs()
+    results = {}
+    for mode in ("fp32", "fp64"):
+        def make():
+            o = sc.apply_to_batched(BatchedOptim(lib, batch=B, horizon_max=T), pb)
+            o.precision = mode
+            o.line_search_rounds, o.keep_previous, o.keep_records = 2, False, False
+            o._meas = o._x[0].clone()                         # measured state (X, B)
+            o._u0 = o._u.clone()
+            o._hist = torch.from_numpy(hist).to(o.device)
+            o._zero_u = torch.zeros((o.U, B), dtype=torch.float64, device=o.device)
+            o._roll = torch.empty_like(o._meas)
+            return o
+
+        def body(slot):
+            o = slot.opt
+            o._roll.copy_(o._meas)
+            for k in range(steps_dt):                         # dead-time roll-forward
+                o._roll[3].copy_(o._hist[0, k]); o._roll[5].copy_(o._hist[1, k])
+                o.dynamics_soa(o._roll, o._zero_u, 0, cycle, out=o._roll)
+            o._x[0].copy_(o._roll); o._u.copy_(o._u0)
+            o.lagrange_multiplier = 0.0; o.mu = 0.0; o.mu_step = 0
+            o.update()
+
+        pipe = graph_pipeline(make, depth, body)
+        steps = 6 * depth
+        ms = time_pipeline(pipe, steps, 1)
+        o = pipe.slots[0].opt
+        results[mode] = (o.x[:64].cpu().numpy(), o.u[:64].cpu().numpy(), o.traj_costs[:64].cpu().numpy(),
+                         o.iterations[:64].cpu().numpy())
+        iters = float(o.iterations.double().mean())
+        by = algorithmic_bytes(o, T, iters, True, fp32=(mode == "fp32")) * steps
+        out[mode] = {"value": B * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+                     "mean_iterations": iters,
+                     "roofline": {"hbm": {"achieved": by / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                          "frac": by / (ms * 1e-3) / 1e9 / hbm, "peak_source": src}}}
+        if mode == "fp64":
+            fl = algorithmic_flops(o, MODEL, T, 1) * steps
+            out[mode]["roofline"]["fp64"] = {"achieved": fl / (ms * 1e-3) / 1e12, "peak": peak_fp64,
+                                             "unit": "TFLOP/s", "frac": fl / (ms * 1e-3) / 1e12 / peak_fp64}
+        del pipe
+        torch.cuda.empty_cache()
+    # the reference (fp64) doing the same for the first 64 scenarios
+    factory, kind = cpu_solver_factory(MODEL)
+    err = {"fp32": 0.0, "fp64": 0.0}
+    same_it = {"fp32": 0, "fp64": 0}
+    n_ref = 64
+    for i in range(n_ref):
+        o = sc.apply_to_single(factory(), pb, i)
+        xo = pb.x0[i].copy()
+        for k in range(steps_dt):
+            xo[3], xo[5] = hist[0, k, i], hist[1, k, i]
+            xo = o.dynamics(xo, np.zeros(2), 0, cycle)
+        o.x[0] = xo
+        o.update()
+        for mode, (gx, gu, gc, gi) in results.items():
+            e = max(np.max(np.abs(gx[i] - np.asarray(o.x))) / np.max(np.abs(np.asarray(o.x))),
+                    np.max(np.abs(gu[i] - np.asarray(o.u))) / max(np.max(np.abs(np.asarray(o.u))), 1e-300),
+                    abs(gc[i] - o.traj_costs) / abs(o.traj_costs))
+            err[mode] = max(err[mode], float(e))
+            same_it[mode] += int(gi[i]) == int(o.iterations)
+    out["workload"] = (f"{B} {MODEL} problems, N={T}, max_iterations={I} (default stop rule 1e-6), HEUN, "
+                       f"{steps_dt} batched dynamics() steps of {cycle} s before every solve, ref_t_offset "
+                       f"{steps_dt * cycle:.2f}, {depth} batches in flight; the timed step includes the roll-forward")
+    out["against_fp64_reference"] = {"problems": n_ref, "cpu_kind": kind,
+                                     "fp32_worst_rel": err["fp32"], "fp64_worst_rel": err["fp64"],
+                                     "fp32_same_iteration_count": same_it["fp32"] / n_ref,
+                                     "fp64_same_iteration_count": same_it["fp64"] / n_ref}
+    out["cpu_baseline"] = cpu_sample(pb, 512, os.cpu_count() or 1, "the same batch (solve only)")
+    return out
 
 
 def single_solve_latency(lib, pb, reps=200, cpu=True):

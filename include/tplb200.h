@@ -93,11 +93,12 @@ typedef struct {
     int32_t integrator_type;       /* integratorType */
     int32_t use_quadratic_terms;   /* useQuadraticTerms: 1 = iLQR, 0 = gradient-only ilr */
     int32_t keep_previous;         /* 1: maintain prev_x / prev_k on accepted steps */
-    int32_t precision;             /* TPLB_FP64 (default, the reference's arithmetic) or TPLB_FP32:
-                                      kernels compute in fp32 and keep their scratch (derivative
-                                      records, line-search candidates) in fp32; every array of this
-                                      struct, the cost sums and the accept / stop decisions stay fp64.
-                                      Needs locally centred coordinates. */
+    int32_t precision;             /* TPLB_FP64 (default, the reference's arithmetic) or TPLB_FP32: the search
+                                      direction — derivative records, Riccati recursion, gains — is computed
+                                      (and the records stored) in fp32; rollouts, stage costs, cost sums, the
+                                      accept / stop decisions and every array of this struct stay fp64, so the
+                                      iteration converges to the fp64 solution.  Needs locally centred
+                                      coordinates. */
     int32_t line_search_rounds;    /* how the 8 step sizes of optim.c:859-873 are rolled out; the accepted
                                       step is the reference's in every mode (bit-identical results):
                                       1 = all 8 at once (lowest latency of one batch),

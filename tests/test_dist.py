@@ -54,6 +54,17 @@ def _worker(rank, world, port, out):
         lo, hi = tdist.shard_range(7, rank, world)
         g2 = tdist.gather_costs(costs[lo:hi], counts=[4, 3])
         ok = ok and torch.equal(torch.nan_to_num(g2, nan=-1.0), torch.nan_to_num(costs[:7], nan=-1.0))
+        # uneven scene shards: 5 scenes on 2 ranks (3 + 2); the per-scene best still arrives in scene order
+        scenes2 = 5
+        counts = [hi - lo for lo, hi in (tdist.shard_range(scenes2, r, world) for r in range(world))]
+        (s_lo, s_hi), (p_lo, p_hi) = tdist.shard_scenes(scenes2, per, rank, world)
+        local = costs[p_lo:p_hi]
+        safe = torch.where(torch.isfinite(local), local, torch.full_like(local, float("inf")))
+        mn, am = safe.view(-1, per).min(dim=1)
+        am = (am + torch.arange(s_hi - s_lo) * per).to(torch.int32)
+        gmin, garg = tdist.gather_best(mn, am, p_lo, counts=counts)
+        ok = ok and counts == [3, 2] and torch.equal(gmin, wmin[:scenes2])
+        ok = ok and torch.equal(garg, (warg + torch.arange(scenes) * per)[:scenes2])
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

@@ -411,44 +411,32 @@ def test_user_defined_problem_through_genopt_build(tmp_path, oracle_libs):
 
 @pytest.mark.parametrize("rounds", [0, 2])
 def test_fp32_mode_against_fp64_oracle(rounds, solver_libs, oracle_libs, cpu_solver):
-    """Optional fp32 compute mode (BASELINE.json configs[4]): kernels compute in single
-    precision and keep derivative records and candidates in fp32; x, u, gains, cost sums and the
-    accept / stop decisions stay fp64.  Stated tolerance
-    5e-4 relative on states, controls and cost against the fp64 CPU oracle after 6 forced
-    iterations (measured 1.5e-4 on B200; BASELINE.json suggests 1e-4, which single-precision
-    Riccati sweeps with 1e4 penalty weights do not reach), for locally centred coordinates;
-    iteration counts are compared and the match rate reported."""
+    """Optional fp32 compute mode (BASELINE.json configs[4], "within a stated 1e-4"): the search
+    direction — derivative records, Riccati recursion, gains — is computed in single precision,
+    while rollouts, stage costs, cost sums and the accept / stop decisions stay fp64.  An inexact
+    Newton direction changes the path of the iteration, not its fixed point, so the converged
+    solution agrees with the reference's fp64 solver: stated tolerance 1e-4 relative on states,
+    controls and cost with the default stop rule, identical iteration count and termination flag
+    for at least 95 % of the problems (locally centred coordinates)."""
     from tpl_b200 import scenarios as sc
-    pb = sc.mpc_time(batch=256, horizon=40, max_iterations=6, forced=True, seed0=4000)
+    pb = sc.mpc_time(batch=128, horizon=40, max_iterations=20, forced=False, seed0=5000)
     pb.scalars["ref_t_offset"][:] = 0.18
     q = sc.apply_to_batched(_factory(solver_libs, pb, rounds)(), pb)
     q.precision = "fp32"
     q.update()
-    worst = 0.0
-    for i in range(0, pb.batch, 16):
-        o = sc.apply_to_single(cpu_solver(pb.model)(), pb, i)
-        o.update()
-        ex = common.rel_err(q.x[i].cpu().numpy(), np.asarray(o.x))
-        eu = np.max(np.abs(q.u[i].cpu().numpy() - np.asarray(o.u))) / max(np.max(np.abs(o.u)), 1.0)
-        ec = abs(float(q.traj_costs[i]) - o.traj_costs) / abs(o.traj_costs)
-        worst = max(worst, ex, eu, ec)
-    print(f"fp32 mode: worst relative deviation from the fp64 oracle {worst:.2e}")
-    assert worst <= 5e-4
-
-    # default mode: relative-change stop; iteration counts and flags versus the oracle
-    pb = sc.mpc_time(batch=128, horizon=40, max_iterations=20, forced=False, seed0=5000)
-    q = sc.apply_to_batched(_factory(solver_libs, pb, rounds)(), pb)
-    q.precision = "fp32"
-    q.update()
-    same = 0
+    same, worst = 0, 0.0
     for i in range(pb.batch):
         o = sc.apply_to_single(cpu_solver(pb.model)(), pb, i)
         o.update()
         same += int(int(q.iterations[i]) == int(o.iterations)
                     and int(q.termination_condition[i]) == int(o.termination_condition))
-        assert abs(float(q.traj_costs[i]) - o.traj_costs) <= 1e-4 * abs(o.traj_costs)
-    print(f"fp32 mode: identical iteration count and flag for {same}/{pb.batch} problems")
-    assert same >= pb.batch * 3 // 4
+        worst = max(worst, common.rel_err(q.x[i].cpu().numpy(), np.asarray(o.x)),
+                    common.rel_err(q.u[i].cpu().numpy(), np.asarray(o.u)),
+                    abs(float(q.traj_costs[i]) - o.traj_costs) / abs(o.traj_costs))
+    print(f"fp32 mode vs fp64 reference: worst relative error {worst:.2e}, identical iteration count and flag "
+          f"for {same}/{pb.batch} problems")
+    assert worst <= 1e-4
+    assert same >= 0.95 * pb.batch
     # the fp64 path is untouched by the precision switch
     q64 = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
     q64.update()

@@ -589,6 +589,22 @@ class BatchedOptim:
         res = out.t()
         return res[0] if single else res
 
+    def dynamics_soa(self, x, u, t, dt, out=None, continuous=False):
+        """``dynamics`` on device tensors already in the solver's layout: ``x`` (X, n), ``u`` (U, n)
+        -> (X, n), no transposes or host traffic (the MPC's dead-time roll-forward calls it
+        ~18 times per control cycle, model_predictive_controller_time.py:159-171).  ``out`` may
+        alias ``x``."""
+        self._require_cuda("dynamics_soa()")
+        if x.shape[0] != self.X or u.shape != (self.U, x.shape[1]) or not (x.is_contiguous() and u.is_contiguous()):
+            raise ValueError(f'Expected contiguous x ({self.X}, n) and u ({self.U}, n), found {tuple(x.shape)}, {tuple(u.shape)}')
+        out = torch.empty_like(x) if out is None else out
+        with torch.cuda.device(self.device):
+            q = self._descriptor()
+            _cabi.check(self._lib, self._lib.tplb_dynamics(
+                C.byref(q), x.data_ptr(), u.data_ptr(), None, x.shape[1], int(t), float(dt),
+                int(continuous), out.data_ptr(), self._stream()), "tplb_dynamics")
+        return out
+
     def dynamics(self, x, u, t, dt):
         """Discrete dynamics with the current integrator: ``(X,)`` or ``(n, X)``
         states (point i uses the scene of problem i when n == batch)."""

@@ -198,8 +198,10 @@ bool throughput_sequence(const tplb_batch& q) {
 template <typename R>
 int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof);
 
-// precision 0: every kernel computes in fp64; 1: the kernels compute in fp32 (storage, cost
-// sums and all accept / stop decisions stay fp64)
+// precision 0: every kernel computes in fp64; 1: the SEARCH DIRECTION (derivative records, Riccati
+// recursion, gains) is computed in fp32, while rollouts, stage costs, cost sums and every accept /
+// stop decision stay fp64 — an inexact Newton direction changes the path of the iteration, not
+// the point it converges to
 // ---- one launch, one thread block per problem (solo.cuh) --------------------------------------
 size_t solo_smem_limit() {
     static int limit = -1;                                 // of the first device used; B200 boxes are uniform
@@ -276,7 +278,7 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
     const size_t cx_stride = (size_t)(q.t_max + 1) * Model::X * B;
     const size_t cu_stride = (size_t)q.t_max * Model::U * B;
     constexpr int R1 = tplb::kRound1, R2 = tplb::kAlphas - tplb::kRound1;
-    using SC = tplb::scratch_t<R>;                         // storage of records and candidates
+    using SC = double;                                     // storage of the line-search candidates
     // Two launch sequences with identical results:
     //   latency    — the batch cannot fill the GPU: fewest launches.  All 8 step sizes roll out at
     //                once, stage costs of the candidates in stage-parallel kernels, the accepted
@@ -296,8 +298,8 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
     prof.after(TPLB_K_STAGE_CONSTS);
 
     prof.before();
-    launch_rollout<R, 1, true>(q, ws, st, 0, nullptr);
-    tplb::stage_cost_kernel<Model, R, double><<<dim3(sgx, T + 1, 1), sb, 0, st>>>(
+    launch_rollout<double, 1, true>(q, ws, st, 0, nullptr);
+    tplb::stage_cost_kernel<Model, double, double><<<dim3(sgx, T + 1, 1), sb, 0, st>>>(
         q, ws, (const double*)q.x, (const double*)q.u, 0, 0, 0, 0, nullptr);
     tplb::init_cost_kernel<<<sgx, sb, 0, st>>>(q, ws);
     prof.after(TPLB_K_ROLLOUT_INIT);
@@ -305,7 +307,7 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
     int lg = 0;
     for (; lg < q.max_lg_iterations; ++lg) {
         prof.before();
-        tplb::multiplier_kernel<Model, R><<<dim3(sgx, Model::C > 0 ? T : 1), sb, 0, st>>>(q, ws);
+        tplb::multiplier_kernel<Model, double><<<dim3(sgx, Model::C > 0 ? T : 1), sb, 0, st>>>(q, ws);
         prof.after(TPLB_K_MULTIPLIER);
         for (int s = 0; s < q.max_iterations; ++s) {
             if (fused_sweep) {
@@ -331,31 +333,31 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
             if (throughput) {
                 // round 1: alpha = 1, 0.1; round 2: the other six for the problems still pending
                 prof.before();
-                launch_rollout<R, R1, false, true>(q, ws, st, 0, nullptr);
+                launch_rollout<double, R1, false, true>(q, ws, st, 0, nullptr);
                 prof.after(TPLB_K_ROLLOUT);
                 prof.before();
                 tplb::select_kernel<PB, 1, true><<<(B + PB - 1) / PB, dim3(PB, R1), 0, st>>>(q, ws);
                 prof.after(TPLB_K_SELECT);
                 prof.before();
-                launch_rollout<R, R2, false, true>(q, ws, st, R1, ws.pending);
+                launch_rollout<double, R2, false, true>(q, ws, st, R1, ws.pending);
                 prof.after(TPLB_K_ROLLOUT);
                 prof.before();
                 tplb::select_kernel<PB, 2, true><<<(B + PB - 1) / PB, dim3(PB, R2), 0, st>>>(q, ws);
                 prof.after(TPLB_K_SELECT);
             } else {
                 prof.before();
-                launch_rollout<R, tplb::kAlphas, false>(q, ws, st, 0, nullptr);
+                launch_rollout<double, tplb::kAlphas, false>(q, ws, st, 0, nullptr);
                 prof.after(TPLB_K_ROLLOUT);
                 // round 1: alpha = 1, 0.1
                 prof.before();
-                tplb::stage_cost_round1_kernel<Model, R><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
+                tplb::stage_cost_round1_kernel<Model, double><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
                 prof.after(TPLB_K_STAGE_COST);
                 prof.before();
                 tplb::select_kernel<PB, 1><<<(B + PB - 1) / PB, dim3(PB, R1), 0, st>>>(q, ws);
                 prof.after(TPLB_K_SELECT);
                 // round 2: alpha = 1e-2 .. 1e-7 for the problems still pending
                 prof.before();
-                tplb::stage_cost_kernel<Model, R, SC><<<dim3(sgx < 8 ? sgx : 8, T + 1, R2), sb, 0, st>>>(
+                tplb::stage_cost_kernel<Model, double, SC><<<dim3(sgx < 8 ? sgx : 8, T + 1, R2), sb, 0, st>>>(
                     q, ws, (const SC*)tplb::scratch<SC>(ws.cand_x), (const SC*)tplb::scratch<SC>(ws.cand_u), cx_stride,
                     cu_stride, 1, R1, ws.pending);
                 prof.after(TPLB_K_STAGE_COST);

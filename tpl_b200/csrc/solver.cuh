@@ -55,10 +55,10 @@ __device__ __forceinline__ int problem_of(const int32_t* list, const int32_t* co
     return idx < *count ? list[idx] : -1;
 }
 
-// Scratch that never leaves the solver — derivative records and line-search candidates, the two
-// widest streams of an iteration — is stored in the compute type: fp64, or fp32 in TPLB_FP32 mode
-// (the buffers keep their fp64 size; fp32 uses the first half).  x, u, k, K, multipliers, cost
-// terms and sums are fp64 in both modes.
+// The derivative records never leave the solver and are stored in the type they are computed
+// in: fp64, or fp32 in TPLB_FP32 mode (the buffer keeps its fp64 size; fp32 uses the first half).
+// Everything else — x, u, k, K, multipliers, line-search candidates, cost terms and sums — is fp64
+// in both modes.
 template <typename R> struct Scratch { using type = double; };
 template <> struct Scratch<float> { using type = float; };
 template <typename R> using scratch_t = typename Scratch<R>::type;
@@ -626,8 +626,8 @@ __device__ __forceinline__ void dev_linearize(const tplb_batch& q, const Workspa
         // the step accepted by the previous line search becomes the trajectory (optim.c:844-848)
         const int win = ws.winner[b];
         if (win >= 0) {
-            const scratch_t<R>* cx = scratch<scratch_t<R>>(ws.cand_x) + (size_t)win * (q.t_max + 1) * X * B + b;
-            const scratch_t<R>* cu = scratch<scratch_t<R>>(ws.cand_u) + (size_t)win * q.t_max * U * B + b;
+            const double* cx = ws.cand_x + (size_t)win * (q.t_max + 1) * X * B + b;
+            const double* cu = ws.cand_u + (size_t)win * q.t_max * U * B + b;
 #pragma unroll
             for (int i = 0; i < X; ++i) {
                 const size_t idx = ((size_t)t * X + i) * B + b;
@@ -1035,7 +1035,8 @@ __device__ __forceinline__ void stage_record(const PV& P, const R* x, const R* u
 template <typename M, typename R, bool kAccept>
 __device__ __forceinline__ void dev_sweep(const tplb_batch& q, const Workspace& ws, int b, int iteration) {
     using D = Dims<M>;
-    using S = scratch_t<R>;
+    using S = double;                            // line-search candidates are fp64 in every mode
+    using SR = scratch_t<R>;                     // derivative records: storage type of the compute precision
     constexpr int X = D::X, U = D::U, C = D::C, NC = D::COMPACT, NSC = D::NSC;
     const int B = q.batch, T = q.horizon;
     const int win = kAccept ? ws.winner[b] : -1;
@@ -1150,9 +1151,9 @@ __device__ __forceinline__ void dev_sweep(const tplb_batch& q, const Workspace& 
         R rec[NC];
         stage_record<M, R>(P, x, u, lam, w, sc, R(t), dt, rec);
         if (q.keep_records) {
-            S* out = scratch<S>(ws.deriv) + (size_t)t * NC * B + b;
+            SR* out = scratch<SR>(ws.deriv) + (size_t)t * NC * B + b;
 #pragma unroll
-            for (int s = 0; s < M::DERIV_COMPACT; ++s) __stcs(out + (size_t)s * B, (S)rec[s]);
+            for (int s = 0; s < M::DERIV_COMPACT; ++s) __stcs(out + (size_t)s * B, (SR)rec[s]);
         }
 
         R k[U], K[U][X];
@@ -1164,7 +1165,7 @@ __device__ __forceinline__ void dev_sweep(const tplb_batch& q, const Workspace& 
             for (int j = 0; j < X; ++j) q.K[((size_t)t * U * X + d * X + j) * B + b] = K[d][j];
         }
     }
-    if (q.keep_records && b == 0) *ws.records_f32 = sizeof(S) == sizeof(float);
+    if (q.keep_records && b == 0) *ws.records_f32 = sizeof(SR) == sizeof(float);
 }
 
 template <typename M, typename R, bool kAccept>
