@@ -329,6 +329,7 @@ def run_ours(a):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(max(a.warmup, depth)):
             step()
+        final_gather()                                   # warm-up of the collective too (NCCL connects lazily)
         pipe.join()
         barrier()
         if clk:

@@ -18,11 +18,15 @@ ap.add_argument("--batch", type=int, default=4096)
 ap.add_argument("--horizon", type=int, default=100)
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--rounds", type=int, default=0)
+ap.add_argument("--keep", type=int, default=0, help="keep_previous / keep_records")
+ap.add_argument("--single-launch", type=int, default=-1)
 a = ap.parse_args()
 
 pb = sc.mpc_time(batch=a.batch, horizon=a.horizon, max_iterations=a.iters, forced=True)
 opt = sc.apply_to_batched(BatchedOptim(build.zoo_library_path(a.model), batch=a.batch, horizon_max=a.horizon), pb)
 opt.line_search_rounds = a.rounds
+opt.keep_previous = opt.keep_records = bool(a.keep)
+opt.single_launch = a.single_launch
 x0, u0 = opt._x[0].clone(), opt._u.clone()
 opt.update()
 torch.cuda.synchronize()

@@ -172,21 +172,39 @@ _RSQRT = sp.Function("m_rsqrt")
 _INV = sp.Function("m_inv")
 
 
-def _strength_reduce(printer, e):
+def _strength_reduce(exprs):
     """CUDA dialect only, applied to the already CSE'd expressions right before printing:
 
-    * ``b**(-1/2)``  -> ``m_rsqrt(b)``  (one MUFU + Newton steps instead of sqrt + divide);
-    * ``b**(-n)``    -> ``m_inv(b**n)``: every division becomes a multiplication by a
-      straight-line reciprocal.  Reciprocals of parameter-only expressions are loop invariant,
-      so the compiler hoists them out of the stage loops entirely.  (sympy prints negative
-      powers inside a product as a division, so this is a tree rewrite, not a printer hook.)
+    * ``b**(-1/2)`` -> ``m_rsqrt(b)`` (one MUFU + Newton steps instead of sqrt + divide), and
+      ``b**(-3/2)`` -> ``m_rsqrt(b)**3``;
+    * ``b**(-n)``   -> ``m_inv(b)**n``: every division becomes a multiplication by a straight-line
+      reciprocal, and all negative powers of one base share ONE reciprocal (the bicycle models
+      use 1/b, 1/b^2, 1/b^3, 1/b^4 of the same two sums) — ``m_rsqrt(b)**(2n)`` where the
+      reciprocal root of ``b`` is needed anyway.  Reciprocals of parameter-only expressions are
+      loop invariant, so the compiler hoists them out of the stage loops entirely.
+      (sympy prints negative powers inside a product as a division, so this is a tree rewrite,
+      not a printer hook.)
 
-    ``a * (1/b)`` differs from ``a / b`` by at most one ulp."""
-    e = e.replace(lambda p: isinstance(p, sp.Pow) and p.exp == sp.Rational(-1, 2),
-                  lambda p: _RSQRT(p.base))
-    e = e.replace(lambda p: isinstance(p, sp.Pow) and p.exp.is_number and p.exp.is_negative,
-                  lambda p: _INV(sp.Pow(p.base, -p.exp)))
-    return e
+    Every rewritten factor differs from the division it replaces by a few ulp at most."""
+    half, three_half = sp.Rational(-1, 2), sp.Rational(-3, 2)
+    pows = set()
+    for e in exprs:
+        pows |= e.atoms(sp.Pow)
+    rs_bases = {p.base for p in pows if p.exp in (half, three_half)}
+
+    def rewrite(p):
+        b, x = p.base, p.exp
+        if x == half:
+            return _RSQRT(b)
+        if x == three_half:
+            return sp.Pow(_RSQRT(b), 3)
+        if x.is_Integer:
+            n = -int(x)
+            return sp.Pow(_RSQRT(b), 2 * n) if b in rs_bases else sp.Pow(_INV(b), n)
+        return _INV(sp.Pow(b, -x))
+
+    return [e.replace(lambda p: isinstance(p, sp.Pow) and p.exp.is_number and p.exp.is_negative, rewrite)
+            for e in exprs]
 
 
 def _pair_sincos(exprs):
@@ -226,8 +244,9 @@ def print_body(printer: ModelPrinter, outputs: Sequence[Tuple[str, sp.MatrixBase
         common, reduced = [], []
 
     if printer.dialect.name == "cuda":
-        common = [(sym, _strength_reduce(printer, e)) for sym, e in common]
-        reduced = [_strength_reduce(printer, e) for e in reduced]
+        rewritten = _strength_reduce([e for _, e in common] + list(reduced))
+        common = [(sym, e) for (sym, _), e in zip(common, rewritten)]
+        reduced = rewritten[len(common):]
 
     # definitions in dependency order: CSE temporaries and sincos pairs
     defs = {}
