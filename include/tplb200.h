@@ -223,6 +223,11 @@ TPLB_API int32_t tplb_linearize(const tplb_batch* batch, void* stream);
  * show after update(), optim.c:1663-1669) into batch->deriv_dense. */
 TPLB_API int32_t tplb_expand_derivatives(const tplb_batch* batch, void* stream);
 
+/* next_x [t_max+1][X][B] / next_u [t_max][U][B] of the reference (optim.c:1657-1659): for every problem the
+ * trajectory its last line search ended on — the accepted step, or the alpha = 1e-7 candidate after
+ * a failed search; zeros before the first search. */
+TPLB_API int32_t tplb_next_trajectory(const tplb_batch* batch, double* next_x, double* next_u, void* stream);
+
 /* Warm-start shift by `amount` stages for all problems, or by amounts[b] when
  * `amounts` (device, [B]) is not NULL (optim.c:1162-1177). */
 TPLB_API int32_t tplb_shift(const tplb_batch* batch, int32_t amount, const int32_t* amounts, void* stream);

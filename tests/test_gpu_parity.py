@@ -114,6 +114,25 @@ def test_cuda_matches_reference_extra_cases(single_launch, solver_libs, tmp_path
     assert not bad, bad[:5]
 
 
+@pytest.mark.parametrize("rounds", [0, 2, "solo"])
+def test_next_trajectory_and_prev_views(rounds, solver_libs, cpu_solver):
+    """next_x / next_u (optim.c:1657-1659) hold the trajectory the last line search ended on,
+    prev_x / prev_k the state before the last accepted step (optim.c:844-845), prev_u is never
+    written by the solver — all against the reference's own arrays."""
+    from tpl_b200 import scenarios as sc
+    pb = sc.mpc_time(batch=6, horizon=50, max_iterations=3, forced=True, seed0=4242)
+    q = sc.apply_to_batched(_factory(solver_libs, pb, rounds)(), pb)
+    q.update()
+    for i in range(pb.batch):
+        o = sc.apply_to_single(cpu_solver(pb.model)(), pb, i)
+        o.update()
+        for n in ("next_x", "next_u", "prev_x", "prev_k", "prev_u"):
+            assert common.rel_err(getattr(q, n)[i].cpu().numpy(), np.asarray(getattr(o, n))) <= common.RTOL, n
+    assert torch.equal(q.next_x, q.x) and torch.equal(q.next_u, q.u)          # every last search accepted a step
+    assert float(q.prev_u.abs().max()) == 0.0
+    assert tuple(q.next_int_step.shape) == (pb.batch, pb.horizon + 1)
+
+
 def test_shift_and_dynamics(solver_libs, oracle_libs, cpu_solver):
     from tpl_b200 import scenarios as sc
     pb = sc.mpc_time(batch=4, horizon=30, max_iterations=3, forced=True, seed0=77)

@@ -160,3 +160,40 @@ def test_generated_headers_are_current():
         first, rest = text.split("\n", 1)
         with open(os.path.join(build.GENERATED, name + ".cuh")) as fd:
             assert fd.read() == first + "\n// generator sha1: " + gen + "\n" + rest, name
+
+
+def test_unsupported_lookups_are_rejected_at_derive_time():
+    """`blerp` / `lerp_wrap` (optim.c:410-486) have no device implementation: a problem definition
+    using them fails with a clear error when it is derived, not inside nvcc."""
+    import sympy as sp
+    from tpl_b200 import derive, genopt, symext as spx
+    x, u, t, dt = sp.symbols("x u t dt")
+    grid, xs = spx.ArraySymbol("grid"), spx.ArraySymbol("xs")
+    for bad in (spx.blerp(0.0, 0.0, 1.0, 1.0, x, t * dt, grid), spx.lerp_wrap(10.0, 1.0, x, xs, grid)):
+        cfg = genopt.Config([x], [u], [grid, xs], sp.Matrix([u]), (x - bad)**2 + u**2)
+        with pytest.raises(NotImplementedError, match="not supported"):
+            derive.derive(cfg)
+
+
+def test_every_slot_is_readable():
+    """`viz.autogui(opt)` of the reference walks `Optim.__slots__` (optim.c:1736-1782) and reads every
+    name: all of them exist here, with the reference's shapes behind a leading batch dimension."""
+    from tpl_b200 import build
+    lib = build.build_zoo(["trajectory_tracking_mpc_time"])["trajectory_tracking_mpc_time"]
+    q = BatchedOptim(lib, batch=3, horizon_max=30, device="cpu")
+    q.horizon = 25
+    B, T, X, U, C = 3, 25, q.X, q.U, q.C
+    want = {"x": (B, T + 1, X), "next_x": (B, T + 1, X), "prev_x": (B, T + 1, X), "u": (B, T, U), "next_u": (B, T, U),
+            "prev_u": (B, T, U), "prev_k": (B, T, U), "k": (B, T, U), "g": (B, T, U), "K": (B, T, U, X),
+            "int_step": (B, T + 1), "next_int_step": (B, T + 1), "fx": (B, T, X, X), "fu": (B, T, X, U),
+            "lx": (B, T, X), "lu": (B, T, U), "lxx": (B, T, X, X), "luu": (B, T, U, U), "lux": (B, T, U, X),
+            "lagrange_multiplier": (B, T, C), "barrier_weight": (B, C), "lg_mult_limit": (B, C),
+            "u_min": (B, T, U), "u_max": (B, T, U)}
+    for name in q.slots:
+        value = getattr(q, name)
+        if name in want:
+            assert tuple(value.shape) == want[name], name
+    assert set(want) <= set(q.slots)
+    q.prev_u = 1.5                                   # writable like every array attribute
+    assert float(q.prev_u.min()) == 1.5
+    assert tuple(q[1].next_x.shape) == (T + 1, X) and tuple(q[1].prev_u.shape) == (T, U)

@@ -55,7 +55,7 @@ EXPORTS = (
     "tplb_abi_version", "tplb_model", "tplb_last_error", "tplb_workspace_bytes",
     "tplb_workspace_counters",
     "tplb_update", "tplb_update_profiled", "tplb_linearize", "tplb_expand_derivatives",
-    "tplb_shift", "tplb_dynamics", "tplb_argmin_groups", "tplb_selftest_math",
+    "tplb_next_trajectory", "tplb_shift", "tplb_dynamics", "tplb_argmin_groups", "tplb_selftest_math",
     "tplb_measure_fp64_tflops",
 )
 
@@ -80,6 +80,8 @@ def load(path):
     for fn in ("tplb_update", "tplb_linearize", "tplb_expand_derivatives"):
         getattr(lib, fn).restype = C.c_int32
         getattr(lib, fn).argtypes = [C.POINTER(Batch), C.c_void_p]
+    lib.tplb_next_trajectory.restype = C.c_int32
+    lib.tplb_next_trajectory.argtypes = [C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.tplb_shift.restype = C.c_int32
     lib.tplb_shift.argtypes = [C.POINTER(Batch), C.c_int32, C.c_void_p, C.c_void_p]
     lib.tplb_dynamics.restype = C.c_int32

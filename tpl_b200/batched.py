@@ -202,9 +202,9 @@ class BatchedOptim:
     EULER, HEUN, RK4 = EULER, HEUN, RK4
 
     # name -> (buffer, rows-extra, component shape fn)
-    _FIELDS = ("x", "u", "prev_x", "prev_k", "k", "K", "g", "lagrange_multiplier",
+    _FIELDS = ("x", "u", "prev_x", "prev_u", "prev_k", "k", "K", "g", "lagrange_multiplier",
                "barrier_weight", "lg_mult_limit", "u_min", "u_max",
-               "fx", "fu", "lx", "lu", "lxx", "luu", "lux", "int_step")
+               "fx", "fu", "lx", "lu", "lxx", "luu", "lux", "int_step", "next_x", "next_u", "next_int_step")
     _STATUS = ("traj_costs", "alpha", "mu", "iterations", "lg_iterations", "mu_step",
                "trajectory_changed", "improved", "termination_condition")
     _SETTINGS = ("dt", "max_iterations", "max_lg_iterations", "min_rel_cost_change",
@@ -236,6 +236,8 @@ class BatchedOptim:
         self._u = z(Tm, U, B, **f64)
         self._prev_x = z(Tm + 1, X, B, **f64)
         self._prev_k = z(Tm, U, B, **f64)
+        self._prev_u = None                # the reference never writes prev_u (optim.c:844-848): zeros on demand
+        self._next = None                  # next_x / next_u, gathered on demand
         self._k = z(Tm, U, B, **f64)
         self._K = z(Tm, U * X, B, **f64)
         self._g = z(Tm, U, B, **f64)
@@ -357,6 +359,13 @@ class BatchedOptim:
             return self._traj_view(self._prev_x, T + 1, (X,))
         if n == "prev_k":
             return self._traj_view(self._prev_k, T, (U,))
+        if n == "prev_u":
+            if self._prev_u is None:
+                self._prev_u = torch.zeros(self.t_max, U, self.batch, dtype=torch.float64, device=self.device)
+            return self._traj_view(self._prev_u, T, (U,))
+        if n in ("next_x", "next_u"):                             # optim.c:1657-1659
+            nx, nu = self._next_trajectory()
+            return self._traj_view(nx, T + 1, (X,)) if n == "next_x" else self._traj_view(nu, T, (U,))
         if n == "k":
             return self._traj_view(self._k, T, (U,))
         if n == "g":
@@ -385,7 +394,7 @@ class BatchedOptim:
             return self._deriv_view(n, (U, U))
         if n == "lux":
             return self._deriv_view(n, (U, X))
-        if n == "int_step":                                       # calcIntStep is always dt (optim.c:636-651)
+        if n in ("int_step", "next_int_step"):                    # calcIntStep is always dt (optim.c:636-651)
             return torch.full((self.batch, T + 1), self.dt, dtype=torch.float64, device=self.device)
         if n in self._STATUS:
             return self._status[n]
@@ -396,7 +405,9 @@ class BatchedOptim:
         raise AttributeError(n)
 
     def __setattr__(self, n, v):
-        if n in self._FIELDS and n != "int_step":
+        if n in ("next_x", "next_u", "int_step", "next_int_step"):
+            raise AttributeError(f"{n} is derived from the last line search and cannot be assigned")
+        if n in self._FIELDS:
             view = getattr(self, n)
             if isinstance(v, (int, float)):
                 view.fill_(float(v))
@@ -418,6 +429,19 @@ class BatchedOptim:
 
     def __len__(self):
         return self.batch
+
+    def _next_trajectory(self):
+        """The candidates the last line searches ended on, gathered into [t][i][B] buffers."""
+        if self._next is None:
+            self._next = (torch.zeros(self.t_max + 1, self.X, self.batch, dtype=torch.float64, device=self.device),
+                          torch.zeros(self.t_max, self.U, self.batch, dtype=torch.float64, device=self.device))
+        if self.device.type == "cuda" and self._workspace is not None:
+            with torch.cuda.device(self.device):
+                q = self._descriptor()
+                _cabi.check(self._lib, self._lib.tplb_next_trajectory(
+                    C.byref(q), self._next[0].data_ptr(), self._next[1].data_ptr(), self._stream()),
+                    "tplb_next_trajectory")
+        return self._next
 
     def set_initial_state(self, x0):
         """``opt.x[:, 0] = x0`` for host or device ``x0`` of shape (B, X)."""

@@ -410,6 +410,16 @@ int32_t tplb_linearize(const tplb_batch* qp, void* stream_) {
     return check_launch("tplb_linearize");
 }
 
+int32_t tplb_next_trajectory(const tplb_batch* qp, double* next_x, double* next_u, void* stream_) {
+    if (int e = validate(qp)) return e;
+    if (!next_x || !next_u) return fail(TPLB_E_ARG, "tplb_next_trajectory: output is NULL");
+    const tplb_batch q = *qp;
+    const tplb::Workspace ws = tplb::carve<Model>(q.workspace, q.batch, q.scenes, q.t_max);
+    const dim3 grid((q.batch + 127) / 128, q.horizon + 1);
+    tplb::next_trajectory_kernel<Model><<<grid, 128, 0, static_cast<cudaStream_t>(stream_)>>>(q, ws, next_x, next_u);
+    return check_launch("tplb_next_trajectory");
+}
+
 int32_t tplb_shift(const tplb_batch* qp, int32_t amount, const int32_t* amounts, void* stream_) {
     if (int e = validate(qp)) return e;
     const tplb_batch q = *qp;

@@ -1409,6 +1409,34 @@ __global__ void accept_kernel(const __grid_constant__ tplb_batch q, Workspace ws
     dev_accept<M, S>(q, ws, b, blockIdx.y);                  // rows 0..T
 }
 
+// next_x / next_u of the reference (optim.c:1657-1659): the trajectory the last line search of each
+// problem ended on — the accepted candidate, or the alpha = 1e-7 one after a failed search.
+// Thread per (problem, stage); rows 0..T.
+template <typename M>
+__global__ void next_trajectory_kernel(const __grid_constant__ tplb_batch q, Workspace ws, double* next_x,
+                                       double* next_u) {
+    using D = Dims<M>;
+    constexpr int X = D::X, U = D::U;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y, B = q.batch;
+    if (b >= B) return;
+    const int a = ws.last_tried[b];
+    const bool have = a >= 0 && a < kAlphas;
+    const double* cx = ws.cand_x + (size_t)(have ? a : 0) * (q.t_max + 1) * X * B + b;
+    const double* cu = ws.cand_u + (size_t)(have ? a : 0) * q.t_max * U * B + b;
+#pragma unroll
+    for (int i = 0; i < X; ++i) {
+        const size_t idx = ((size_t)t * X + i) * B;
+        next_x[idx + b] = have ? cx[idx] : 0.0;
+    }
+    if (t < q.horizon) {
+#pragma unroll
+        for (int d = 0; d < U; ++d) {
+            const size_t idx = ((size_t)t * U + d) * B;
+            next_u[idx + b] = have ? cu[idx] : 0.0;
+        }
+    }
+}
+
 __device__ __forceinline__ void dev_finalize(const tplb_batch& q, int b, int lg_done) {
     q.lg_iterations[b] = lg_done;
     if (q.iterations[b] == q.max_iterations) q.termination_condition[b] = 1;   // optim.c:1147-1149
