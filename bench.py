@@ -87,7 +87,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--line-search-rounds", type=int, default=2, choices=[0, 1, 2],
                     help="tplb_batch.line_search_rounds for the throughput legs (2: least work, for a full GPU)")
-    ap.add_argument("--in-flight", type=int, default=16,
+    ap.add_argument("--in-flight", type=int, default=24,
                     help="batches in flight: solver instances (one CUDA stream each) the steps alternate between")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every launch instead of replaying one CUDA graph per slot")
     ap.add_argument("--skip-configs", action="store_true", help="skip the legs for BASELINE.json configs #3-#5")

@@ -133,6 +133,35 @@ def test_next_trajectory_and_prev_views(rounds, solver_libs, cpu_solver):
     assert tuple(q.next_int_step.shape) == (pb.batch, pb.horizon + 1)
 
 
+@pytest.mark.parametrize("rounds", [0, 2, "solo"])
+def test_per_problem_horizons(rounds, solver_libs, cpu_solver):
+    """`tplb_batch.horizons`: problems of different length in one batch (candidate corridors of
+    different map length, path_optim.py:126) — every problem must come out exactly as the reference
+    solves it alone with its own T, and rows past its horizon stay untouched."""
+    from tpl_b200 import scenarios as sc
+    lengths = [40, 100, 250, 1, 250, 77, 100, 3]
+    pb = sc.lateral(batch=len(lengths), horizon=250, max_iterations=10, forced=False, seed0=3100)
+    q = sc.apply_to_batched(_factory(solver_libs, pb, rounds)(), pb)
+    q.horizons = lengths
+    q.x[:, 1:] = -7.0                                   # sentinel beyond x[0]
+    q.update()
+    for i, T in enumerate(lengths):
+        one = pb.subset([i])
+        one.horizon = T
+        # (the map arrays keep their length: lookups near a shorter horizon read the same samples)
+        one.u0, one.u_min, one.u_max = one.u0[:, :T], one.u_min[:, :T], one.u_max[:, :T]
+        o = sc.apply_to_single(cpu_solver(pb.model)(), one, 0)
+        o.update()
+        assert int(q.iterations[i]) == int(o.iterations), i
+        assert int(q.termination_condition[i]) == int(o.termination_condition), i
+        assert common.rel_err(q.x[i, :T + 1].cpu().numpy(), np.asarray(o.x)) <= common.RTOL, i
+        assert common.rel_err(q.u[i, :T].cpu().numpy().reshape(-1), np.asarray(o.u).reshape(-1)) <= common.RTOL, i
+        assert abs(float(q.traj_costs[i]) - o.traj_costs) <= common.RTOL * abs(o.traj_costs), i
+        assert bool((q.x[i, T + 1:] == -7.0).all()), i   # rows past the problem's horizon are not written
+    with pytest.raises(ValueError):
+        q.horizons = [251] * len(lengths)
+
+
 def test_shift_and_dynamics(solver_libs, oracle_libs, cpu_solver):
     from tpl_b200 import scenarios as sc
     pb = sc.mpc_time(batch=4, horizon=30, max_iterations=3, forced=True, seed0=77)

@@ -254,6 +254,7 @@ class BatchedOptim:
         self._array_index = {n: i for i, n in enumerate(info["array_names"])}
         self._scalars = z(max(1, len(self._scalar_index)), S, **f64)
         self._arrays = [z(S, 0, **f64) for _ in self._array_index]
+        self._horizons = None
         self._workspace = None
         self._deriv_dense = None
         self._deriv_stale = True
@@ -284,8 +285,30 @@ class BatchedOptim:
     @horizon.setter
     def horizon(self, v):
         self._T = min(self.t_max, max(1, int(v)))                 # optim.c:1726-1734
+        if getattr(self, "_horizons", None) is not None and int(self._horizons.max()) > self._T:
+            self._horizons = torch.clamp(self._horizons, max=self._T)
 
     T = horizon
+
+    @property
+    def horizons(self):
+        """Optional per-problem horizons ``T_b`` (B,), each in 1..``horizon`` — every reference
+        ``Optim`` object owns its T (``PathOptim`` sets it from the length of the local map every
+        cycle, path_optim.py:126).  ``None``: all problems use ``horizon``.  Array attributes keep
+        the shape of the largest horizon; rows past a problem's own horizon are not touched."""
+        return self._horizons
+
+    @horizons.setter
+    def horizons(self, v):
+        if v is None:
+            self._horizons = None
+            return
+        h = torch.as_tensor(np.asarray(v.cpu() if isinstance(v, torch.Tensor) else v), dtype=torch.int32)
+        if h.shape != (self.batch,):
+            raise ValueError(f'Expected "horizons" with shape ({self.batch}), but found {tuple(h.shape)}')
+        if int(h.min()) < 1 or int(h.max()) > self._T:
+            raise ValueError(f"horizons must lie in 1..horizon (= {self._T}); set `horizon` to the largest one first")
+        self._horizons = h.to(self.device)
 
     @property
     def step(self):
@@ -513,6 +536,7 @@ class BatchedOptim:
         q.workspace = self._workspace.data_ptr()
         q.workspace_bytes = self._workspace_bytes
         q.deriv_dense = self._deriv_dense.data_ptr() if self._deriv_dense is not None else None
+        q.horizons = self._horizons.data_ptr() if self._horizons is not None else None
         return q
 
     def _require_cuda(self, what):
@@ -690,6 +714,7 @@ class BatchedOptim:
         for n in self._SETTINGS:
             object.__setattr__(o, n, getattr(self, n))
         o._T = self._T
+        o._horizons = None if self._horizons is None else self._horizons.clone()
         if self._workspace is not None:
             o._ensure_workspace()
             o._workspace.copy_(self._workspace)

@@ -260,7 +260,6 @@ int run_update(const tplb_batch* qp, void* stream_, Profiler& prof) {
             return fail(TPLB_E_UNSUPPORTED, "single_launch needs fp64, use_quadratic_terms and a problem that fits shared memory");
         return run_solo(*qp, static_cast<cudaStream_t>(stream_), prof);
     }
-    if (qp->horizons) return fail(TPLB_E_UNSUPPORTED, "per-problem horizons need the single-launch path");
     return qp->precision == TPLB_FP32 ? run_update_as<float>(qp, stream_, prof)
                                       : run_update_as<double>(qp, stream_, prof);
 }

@@ -49,6 +49,13 @@ namespace tplb {
 constexpr int kAlphas = TPLB_LINE_SEARCH_STEPS;
 constexpr int kRound1 = 2;      // step sizes of the first line-search round (alpha = 1, 0.1)
 
+// Horizon of problem b: its own (tplb_batch.horizons, optim.c:508-622 — every reference object owns
+// its T) or the batch's.  Stage-parallel kernels are launched for the largest horizon of the batch
+// (q.horizon) and rows past a problem's own horizon return at once.
+__device__ __forceinline__ int horizon_of(const tplb_batch& q, int b) {
+    return q.horizons ? __ldg(q.horizons + b) : q.horizon;
+}
+
 // Problem handled by work item `idx`: the item itself, or an entry of the pending list.
 __device__ __forceinline__ int problem_of(const int32_t* list, const int32_t* count, int idx, int B) {
     if (!list) return idx < B ? idx : -1;
@@ -324,7 +331,8 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
     } else {
         live = live && ws.running[b];
     }
-    const int T = q.horizon;
+    const int T = q.horizon;                                 // block-uniform loop bound (barriers inside)
+    const int Tb = live ? horizon_of(q, b) : 0;              // this problem's horizon
     const int scene = live ? __ldg(q.scene_index + b) : 0;
     CachedParamView<R, M::NUM_SCALARS> P;                    // scalar parameters in registers for the whole chain
     P.preload(param_view_scene<R>(q, scene));
@@ -373,12 +381,12 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
     int buf = 0;
     for (int t = 0; t < T; ++t) {
         const int nxt = buf + 1 == kRolloutSlots ? 0 : buf + 1;
-        if (live && t + 1 < T) fetch(t + 1, nxt);
+        if (live && t + 1 < Tb) fetch(t + 1, nxt);
         async_commit();                                      // (possibly empty) group of stage t+1
         async_wait_all_but_one();                            // this thread's share of stage t has landed
         __syncthreads();                                     // ... and everybody else's
 
-        if (live) {
+        if (live && t < Tb) {
             const double* in = ring(buf);                    // stage t of this problem, item e at in[e * PB]
             R un[U], xnext[X], sc[D::NSCs];
 #pragma unroll
@@ -425,8 +433,8 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
     }
     if (kCost && live) {
         R sc[D::NSCs], c;
-        load_stage_consts<M, R>(q, ws, scene, T, sc);
-        M::end_cost(P, xn, sc, R(T), R(q.dt), &c);
+        load_stage_consts<M, R>(q, ws, scene, Tb, sc);
+        M::end_cost(P, xn, sc, R(Tb), R(q.dt), &c);
         total += (double)c;
         ws.cand_cost[(size_t)ai * B + b] = total;
     }
@@ -459,7 +467,8 @@ __device__ __forceinline__ void dev_stage_cost(const tplb_batch& q, const Worksp
     constexpr int X = D::X, U = D::U, C = D::C;
     const int B = q.batch;
     if (check_running && !ws.running[b]) return;
-    const int T = q.horizon;
+    const int T = horizon_of(q, b);
+    if (t > T) return;
     const int scene = __ldg(q.scene_index + b);
     const ParamView<R> P = param_view_scene<R>(q, scene);
     const S* xa = xs + a * x_stride + b;
@@ -505,9 +514,11 @@ template <typename M, typename R>
 __global__ void stage_cost_round1_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U, C = D::C;
-    const int B = q.batch, T = q.horizon, t = blockIdx.y;
+    const int B = q.batch, t = blockIdx.y;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B || !ws.running[b]) return;
+    const int T = horizon_of(q, b);
+    if (t > T) return;
     const size_t x_stride = (size_t)(q.t_max + 1) * X * B, u_stride = (size_t)q.t_max * U * B;
     const scratch_t<R>* cand_x = scratch<scratch_t<R>>(ws.cand_x);
     const scratch_t<R>* cand_u = scratch<scratch_t<R>>(ws.cand_u);
@@ -544,7 +555,7 @@ __global__ void stage_cost_round1_kernel(const __grid_constant__ tplb_batch q, W
 __device__ __forceinline__ void dev_init_cost(const tplb_batch& q, const Workspace& ws, int b) {
     const int B = q.batch;
     double total = 0.0;
-    const int T = q.horizon;
+    const int T = horizon_of(q, b);
     for (int t = 0; t <= T; ++t) total += ws.cost_terms[(size_t)t * B + b];
     q.traj_costs[b] = total;
 }
@@ -574,7 +585,7 @@ __device__ __forceinline__ void dev_multiplier(const tplb_batch& q, const Worksp
         for (int c = 0; c < C; ++c) zero = zero && q.lg_mult_limit[(size_t)c * B + b] == 0.0;
         ws.lam_zero[b] = zero;
     }
-    if (C == 0) return;
+    if (C == 0 || t >= horizon_of(q, b)) return;
     const int scene = __ldg(q.scene_index + b);
     const ParamView<R> P = param_view_scene<R>(q, scene);
     R x[X], u[U], lam[D::Cs], w[D::Cs], g[D::Cs], sc[D::NSCs];
@@ -618,7 +629,8 @@ __device__ __forceinline__ void dev_linearize(const tplb_batch& q, const Workspa
     using D = Dims<M>;
     constexpr int X = D::X, U = D::U, C = D::C;
     const int B = q.batch;
-    const int T = q.horizon;
+    const int T = horizon_of(q, b);
+    if (t > T) return;
 
     R x[X], u[U];
     bool have = false;
@@ -648,8 +660,8 @@ __device__ __forceinline__ void dev_linearize(const tplb_batch& q, const Workspa
             }
             have = true;
         }
-        if (t >= T) return;
     }
+    if (t >= T) return;
     if (!kForce && !(ws.running[b] && q.trajectory_changed[b])) return;
     const int scene = __ldg(q.scene_index + b);
     const ParamView<R> P = param_view_scene<R>(q, scene);
@@ -950,7 +962,7 @@ __device__ __forceinline__ void dev_backward(const tplb_batch& q, const Workspac
     q.trajectory_changed[b] = 0;                 // optim.c:911 (linearize_kernel ran just before)
     const int scene = __ldg(q.scene_index + b);
     const ParamView<R> P = param_view_scene<R>(q, scene);
-    const int T = q.horizon;
+    const int T = horizon_of(q, b);
     const double mu = q.mu[b];
 
     R Vx[X], Vxx[X][X];
@@ -1038,7 +1050,7 @@ __device__ __forceinline__ void dev_sweep(const tplb_batch& q, const Workspace& 
     using S = double;                            // line-search candidates are fp64 in every mode
     using SR = scratch_t<R>;                     // derivative records: storage type of the compute precision
     constexpr int X = D::X, U = D::U, C = D::C, NC = D::COMPACT, NSC = D::NSC;
-    const int B = q.batch, T = q.horizon;
+    const int B = q.batch, T = horizon_of(q, b);
     const int win = kAccept ? ws.winner[b] : -1;
     const bool run = ws.running[b] != 0;
     if (!run && win < 0) return;
@@ -1191,7 +1203,7 @@ __device__ __forceinline__ void dev_backward_first_order(const tplb_batch& q, co
     q.trajectory_changed[b] = 0;
     const int scene = __ldg(q.scene_index + b);
     const ParamView<R> P = param_view_scene<R>(q, scene);
-    const int T = q.horizon;
+    const int T = horizon_of(q, b);
     R Vx[X];
     {
         R xT[X], Vxx[X * X], sc[D::NSCs];
@@ -1312,7 +1324,7 @@ __device__ __forceinline__ void conclude_line_search(const tplb_batch& q, const 
 
 // cost of candidate a of problem b: the stage terms added in the reference's order
 __device__ __forceinline__ double dev_candidate_total(const tplb_batch& q, const Workspace& ws, int b, int a) {
-    const int B = q.batch, T = q.horizon;
+    const int B = q.batch, T = horizon_of(q, b);
     const double* terms = ws.cost_terms + (size_t)a * (q.t_max + 1) * B + b;
     double total = 0.0;
     int t = 0;
@@ -1383,7 +1395,8 @@ __device__ __forceinline__ void dev_accept(const tplb_batch& q, const Workspace&
     constexpr int X = D::X, U = D::U;
     const int B = q.batch;
     const int win = ws.winner[b];
-    if (win < 0) return;
+    const int T = horizon_of(q, b);
+    if (win < 0 || t > T) return;
     const S* cx = scratch<S>(ws.cand_x) + (size_t)win * (q.t_max + 1) * X * B + b;
     const S* cu = scratch<S>(ws.cand_u) + (size_t)win * q.t_max * U * B + b;
 #pragma unroll
@@ -1392,7 +1405,7 @@ __device__ __forceinline__ void dev_accept(const tplb_batch& q, const Workspace&
         if (q.keep_previous) q.prev_x[idx] = q.x[idx];
         q.x[idx] = (double)cx[((size_t)t * X + i) * B];
     }
-    if (t < q.horizon) {
+    if (t < T) {
 #pragma unroll
         for (int d = 0; d < U; ++d) {
             const size_t idx = ((size_t)t * U + d) * B + b;
@@ -1420,6 +1433,8 @@ __global__ void next_trajectory_kernel(const __grid_constant__ tplb_batch q, Wor
     const int b = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y, B = q.batch;
     if (b >= B) return;
     const int a = ws.last_tried[b];
+    const int T = horizon_of(q, b);
+    if (t > T) return;
     const bool have = a >= 0 && a < kAlphas;
     const double* cx = ws.cand_x + (size_t)(have ? a : 0) * (q.t_max + 1) * X * B + b;
     const double* cu = ws.cand_u + (size_t)(have ? a : 0) * q.t_max * U * B + b;
@@ -1428,7 +1443,7 @@ __global__ void next_trajectory_kernel(const __grid_constant__ tplb_batch q, Wor
         const size_t idx = ((size_t)t * X + i) * B;
         next_x[idx + b] = have ? cx[idx] : 0.0;
     }
-    if (t < q.horizon) {
+    if (t < T) {
 #pragma unroll
         for (int d = 0; d < U; ++d) {
             const size_t idx = ((size_t)t * U + d) * B;
@@ -1461,7 +1476,7 @@ __global__ void shift_kernel(const __grid_constant__ tplb_batch q, int amount, c
     int n = amounts ? amounts[b] : amount;
     if (n < 0) n = 0;
     if (n == 0) return;
-    const int T = q.horizon;
+    const int T = horizon_of(q, b);
     for (int t = 0; t < T + 1; ++t) {
         const int s = (t + n < T) ? t + n : T;
 #pragma unroll
