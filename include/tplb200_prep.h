@@ -31,7 +31,7 @@ extern "C" {
 #define TPLB_PREP_API
 #endif
 
-#define TPLB_PREP_ABI_VERSION 1
+#define TPLB_PREP_ABI_VERSION 2
 enum { TPLB_PREP_E_ARG = -1 };
 
 TPLB_PREP_API int32_t tplb_prep_abi_version(void);
@@ -84,6 +84,34 @@ typedef struct {
 } tplb_ego;
 
 TPLB_PREP_API int32_t tplb_update_ego(const tplb_ego* ego, double t, double dt, void* stream);
+
+/* ---- row f1: reference-path preparation in front of every MPC solve ---------------------------------
+ * util.project (library/src/utils.cpp:257-408; control/model_predictive_controller.py:188-189 takes
+ * x0[5] = arc_len from it) for B (path, position) pairs.  paths [B][points][stride] rows as the reference
+ * holds them (x, y first), position [B][2], out [12][B]: distance, arc_len, alpha, index, start, end,
+ * point x, y, tangent x, y, angle, in_bounds (TPLB_PROJ_*). */
+enum { TPLB_PROJ_DISTANCE = 0, TPLB_PROJ_ARC_LEN, TPLB_PROJ_ALPHA, TPLB_PROJ_INDEX, TPLB_PROJ_START, TPLB_PROJ_END,
+       TPLB_PROJ_POINT_X, TPLB_PROJ_POINT_Y, TPLB_PROJ_TANGENT_X, TPLB_PROJ_TANGENT_Y, TPLB_PROJ_ANGLE,
+       TPLB_PROJ_IN_BOUNDS, TPLB_PROJ_FIELDS };
+TPLB_PREP_API int32_t tplb_project(int32_t batch, int32_t points, int32_t stride, const double* paths,
+                                   const double* position, int32_t closed, double* out, void* stream);
+
+/* util.resample_path = tplcpp.resample (library/src/utils.cpp:410-560) + interp_resampled_path
+ * (library/tpl/util.py:134-191; model_predictive_controller.py:124-128, path_optim.py:307).
+ * paths [B][points][6] (x, y, orientation, s, curvature, velocity); rs [6][B][steps]: every component is a
+ * (B, steps) array that can be bound as a solver parameter (ref_x, ref_y, ...) without a copy;
+ * ok [B]: 0 where the reference returns None (resampling failed) or all points coincide — rs is then
+ * zero; start_index [B] or NULL (= 0); scratch: tplb_resample_scratch_doubles() doubles. */
+TPLB_PREP_API size_t tplb_resample_scratch_doubles(int32_t batch, int32_t points, int32_t steps);
+TPLB_PREP_API int32_t tplb_resample_path(int32_t batch, int32_t points, const double* paths, double step_size,
+                                         int32_t steps, const int32_t* start_index, int32_t zero_vel_at_end,
+                                         int32_t closed, double* rs, int32_t* ok, double* scratch, void* stream);
+
+/* path_optim.py:303-305: the lateral solution back to Cartesian coordinates, in place on paths [B][n][6]:
+ * x += -sin(phi) d, y += cos(phi) d, phi += atan(v_d) with d, v_d = states 0, 1 of the solver's
+ * buffer xs [t][state_dims][B] (tplb_batch.x). */
+TPLB_PREP_API int32_t tplb_frenet_to_cartesian(int32_t batch, int32_t n, int32_t state_dims, double* paths,
+                                               const double* xs, void* stream);
 
 #ifdef __cplusplus
 }

@@ -112,3 +112,55 @@ class EgoOracle:
         fn.argtypes = [C.POINTER(_Ego), C.POINTER(_History), C.POINTER(_History), C.c_double, C.c_double]
         fn.restype = None
         fn(C.byref(self._e), C.byref(self._acc), C.byref(self._steer), float(t), float(dt))
+
+
+# ---- row f1: project / resample / interp_resampled_path -----------------------------------------
+PROJECTION_FIELDS = ("distance", "arc_len", "alpha", "index", "start", "end", "point_x", "point_y",
+                     "tangent_x", "tangent_y", "angle", "in_bounds")
+
+
+def project(points, position, closed=False):
+    """library/src/utils.cpp:257-408 -> dict of the Projection fields."""
+    pts = np.ascontiguousarray(np.asarray(points, dtype=np.float64)[:, :2])
+    out = np.empty(12)
+    fn = lib().tplo_project
+    fn.argtypes = [_D, C.c_int, C.c_double, C.c_double, C.c_int, _D]
+    fn.restype = None
+    fn(pts, len(pts), float(position[0]), float(position[1]), int(bool(closed)), out)
+    return dict(zip(PROJECTION_FIELDS, out))
+
+
+def resample(points, sampling_dist, steps, start_index=0, closed=False):
+    """library/src/utils.cpp:410-560 -> (rows, 5) array x, y, alpha, prev, next, or None where the
+    reference raises RuntimeError."""
+    pts = np.ascontiguousarray(np.asarray(points, dtype=np.float64)[:, :2])
+    rsi = np.zeros((max(int(steps), 1), 5))
+    scratch = np.empty(2 * max(len(pts), 1))
+    fn = lib().tplo_resample
+    fn.argtypes = [_D, C.c_int, C.c_double, C.c_int, C.c_long, C.c_int, _D, _D]
+    fn.restype = C.c_int
+    n = fn(pts, len(pts), float(sampling_dist), int(steps), int(start_index), int(bool(closed)), scratch, rsi)
+    if n < 0:
+        return None
+    return rsi[:n]
+
+
+def interp_resampled_path(path, rsi, step_size, steps, zero_vel_at_end=False, closed=False):
+    """library/tpl/util.py:155-191 -> (steps, 6)."""
+    path = np.ascontiguousarray(path, dtype=np.float64)
+    rsi = np.ascontiguousarray(rsi, dtype=np.float64)
+    rs = np.zeros((int(steps), 6))
+    fn = lib().tplo_interp_resampled_path
+    fn.argtypes = [_D, C.c_int, _D, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, _D]
+    fn.restype = None
+    fn(path, len(path), rsi, len(rsi), float(step_size), int(steps), int(bool(zero_vel_at_end)), int(bool(closed)), rs)
+    return rs
+
+
+def resample_path(path, step_size, steps, start_index=0, zero_vel_at_end=False, closed=False):
+    """library/tpl/util.py:134-152."""
+    path = np.asarray(path, dtype=np.float64)
+    rsi = resample(path[:, :2], step_size, steps, start_index, closed)
+    if rsi is None:
+        return None
+    return interp_resampled_path(path, rsi, step_size, steps, zero_vel_at_end, closed)

@@ -72,6 +72,32 @@ def shift_interp_golden():
     print("shift_interp:", len(ps.shift_cases()), "cases")
 
 
+def resample_path_golden():
+    """util.interp_resampled_path (library/tpl/util.py:155-191, numba) run as it stands on the index
+    tables the C restatement of `resample` produces (the C++ `resample` itself needs Eigen, which is
+    not in this image): tests/golden/prep_path.npz."""
+    from oracle import prep as oprep
+    path = os.path.join(REF, "util.py")
+    norm = reference_function(path, "normalize_angle")
+    import numba
+    src = open(path).read()
+    tree = ast.parse(src)
+    ns = {"numba": numba, "np": np, "normalize_angle": norm}
+    for name in ("short_angle_dist", "interp_resampled_path"):
+        node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
+        deco = "\n".join("@" + ast.get_source_segment(src, d).replace("cache=True, ", "").replace("cache=True", "")
+                         for d in node.decorator_list)
+        exec(compile(deco + "\n" + ast.get_source_segment(src, node), path, "exec"), ns)
+    fn = ns["interp_resampled_path"]
+    out = {}
+    for i, (pth, step, steps, start, zero_end) in enumerate(ps.path_cases()):
+        rsi = oprep.resample(pth[:, :2], step, steps, start, False)
+        out[f"rsi_{i}"] = rsi
+        out[f"rs_{i}"] = fn(np.array(pth), rsi, step, steps, zero_end, False)
+    np.savez_compressed(os.path.join(HERE, "prep_path.npz"), **out)
+    print("resample_path:", len(ps.path_cases()), "cases")
+
+
 def update_ego_golden():
     """SimCore.update_ego (simulation/core.py:91-134) run as it stands: the method is taken from the
     reference file, `util.normalize_angle` from the reference's util.py (numba), `self` and `ego`
@@ -95,6 +121,9 @@ def update_ego_golden():
 
 
 def main():
+    if sys.argv[1:] == ["path"]:
+        return resample_path_golden()
+    resample_path_golden()
     shift_interp_golden()
     update_ego_golden()
     vel = reference_function(os.path.join(REF, "planning", "utils.py"), "rampify_profile")

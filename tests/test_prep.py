@@ -330,3 +330,130 @@ def test_oracle_against_the_live_reference_functions():
         want = lat(c["step"], c["horizon"], c["evasion_sharpness"], c["proj_distance"], c["path"], c["gap"],
                    c["lower"], c["upper"])
         np.testing.assert_allclose(_lat_oracle(c), want, rtol=RTOL, atol=1e-12)
+
+
+# ---- row f1: reference-path preparation (util.resample_path, util.project) ---------------------------
+def test_path_oracle_matches_the_reference_function_and_geometry():
+    """`interp_resampled_path` (util.py:155-191) of the C restatement against the vectors recorded by
+    running the reference's own numba function (prep_path.npz); `resample` / `project` (C++ on Eigen, not
+    buildable here: parity unpinned) through their defining properties — samples exactly `step`
+    apart and on the polyline, the projection is the nearest point of the polyline."""
+    g = np.load(os.path.join(GOLDEN, "prep_path.npz"))
+    for i, (path, step, steps, start, zero_end) in enumerate(ps.path_cases()):
+        rsi = oprep.resample(path[:, :2], step, steps, start, False)
+        np.testing.assert_array_equal(rsi, g[f"rsi_{i}"])
+        rs = oprep.interp_resampled_path(path, rsi, step, steps, zero_end, False)
+        np.testing.assert_allclose(rs, g[f"rs_{i}"], rtol=RTOL, atol=1e-12)
+        gaps = np.linalg.norm(np.diff(rs[:, :2], axis=0), axis=1)
+        np.testing.assert_allclose(gaps, step, rtol=0, atol=1e-12)
+        inside = rsi[:, 2] <= 1.0                               # not extrapolated past the last point
+        a, b = path[rsi[inside, 3].astype(int), :2], path[rsi[inside, 4].astype(int), :2]
+        on_segment = a + rsi[inside, 2:3] * (b - a)
+        np.testing.assert_allclose(rs[inside, :2], on_segment, rtol=0, atol=1e-9)
+    paths, pos = ps.path_batch(16, seed0=40)
+    for b in range(16):
+        pr = oprep.project(paths[b], pos[b])
+        pts = paths[b][:, :2]
+        w = np.linspace(0, 1, 4001)[None, :, None]
+        dense = (pts[:-1, None, :] * (1 - w) + pts[1:, None, :] * w).reshape(-1, 2)
+        dist = np.linalg.norm(dense - pos[b], axis=1)
+        assert abs(abs(pr["distance"]) - dist.min()) < 1e-6
+        seg = np.linalg.norm(np.diff(pts, axis=0), axis=1)
+        k = int(pr["start"])
+        assert abs(pr["arc_len"] - (seg[:k].sum() + pr["alpha"] * seg[k])) < 1e-9
+        # the sign of the distance: positive on the left of the direction of travel
+        t = pts[int(pr["end"])] - pts[k]
+        left = t[0] * (pos[b][1] - pr["point_y"]) - t[1] * (pos[b][0] - pr["point_x"])
+        assert np.sign(pr["distance"]) == np.sign(left)
+
+
+@pytest.mark.gpu
+def test_resample_path_and_project_match_the_oracle(prep_lib):
+    """The batched kernels (tplb_resample_path, tplb_project) against the golden vectors of the
+    reference's `interp_resampled_path` and the C restatement, 1e-9."""
+    g = np.load(os.path.join(GOLDEN, "prep_path.npz"))
+    for i, (path, step, steps, start, zero_end) in enumerate(ps.path_cases()):
+        rs, ok = prep.resample_path(path[None], step, steps, start_index=start, zero_vel_at_end=zero_end)
+        assert bool(ok[0])
+        np.testing.assert_allclose(rs.permute(1, 2, 0)[0].cpu().numpy(), g[f"rs_{i}"], rtol=RTOL, atol=1e-10)
+    paths, pos = ps.path_batch(200, seed0=7)
+    rs, ok = prep.resample_path(paths, 0.5, 100, zero_vel_at_end=True)
+    pr = prep.project(paths, pos)
+    assert bool(ok.all())
+    for b in range(0, 200, 9):
+        want = oprep.resample_path(paths[b], 0.5, 100, 0, True)
+        np.testing.assert_allclose(rs[:, b].t().cpu().numpy(), want, rtol=RTOL, atol=1e-10)
+        o = oprep.project(paths[b], pos[b])
+        for name in prep.PROJECTION_FIELDS:
+            assert abs(float(pr[name][b]) - o[name]) <= 1e-9 * max(1.0, abs(o[name])), (b, name)
+    # a path that is too short to reach its last requested sample on the second-to-last segment keeps
+    # marching on the last one (extrapolation); a degenerate path (all points equal) is reported, not solved
+    same = np.repeat(paths[:1, :1], 20, axis=1)
+    _, ok = prep.resample_path(same, 0.5, 10)
+    assert not bool(ok[0])
+
+
+@pytest.mark.gpu
+def test_mpc_cycle_inputs_stay_on_the_device(prep_lib, solver_libs):
+    """Rows f1 + a: what `ModelPredictiveController.update` does per cycle
+    (control/model_predictive_controller.py:124-193) for a whole batch without leaving the device —
+    resample the planned trajectory, project the vehicle on it, bind the resampled columns as the
+    solver's reference arrays, x0[5] = arc length, solve — against the CPU doing the same per problem."""
+    from oracle import oracle
+    from tpl_b200 import scenarios as sc
+    from tpl_b200.batched import BatchedOptim
+    oracle.build_libs()
+    B, T = 24, 40
+    paths, pos = ps.path_batch(B, seed0=300)
+    rs, ok = prep.resample_path(paths, 0.5, 100, zero_vel_at_end=True)
+    pr = prep.project(rs.permute(1, 2, 0)[:, :, :2].contiguous(), pos)
+    pb = sc.mpc(batch=B, horizon=T, max_iterations=6, forced=True, seed0=300)
+    q = sc.apply_to_batched(BatchedOptim(solver_libs[pb.model], batch=B, horizon_max=T), pb)
+    for col, name in ((0, "ref_x"), (1, "ref_y"), (2, "ref_phi"), (4, "ref_k"), (5, "ref_v")):
+        setattr(q.params, name, rs[col])                         # (B, 100) device arrays, no host round trip
+    x0 = torch.from_numpy(pb.x0).cuda()
+    x0[:, :2] = torch.from_numpy(pos).cuda()
+    x0[:, 2] = pr["angle"]
+    x0[:, 5] = pr["arc_len"]
+    q.set_initial_state(x0)
+    q.update()
+    for b in (0, 11, 23):
+        ref = oprep.resample_path(paths[b], 0.5, 100, 0, True)
+        o = sc.apply_to_single(oracle.OracleOptim(pb.model), pb, b)
+        for col, name in ((0, "ref_x"), (1, "ref_y"), (2, "ref_phi"), (4, "ref_k"), (5, "ref_v")):
+            setattr(o.params, name, ref[:, col])
+        p = oprep.project(ref[:, :2], pos[b])
+        xo = pb.x0[b].copy()
+        xo[:2], xo[2], xo[5] = pos[b], p["angle"], p["arc_len"]
+        o.x[0] = xo
+        o.update()
+        assert int(q.iterations[b]) == int(o.iterations)
+        assert abs(float(q.traj_costs[b]) - o.traj_costs) <= 1e-5 * abs(o.traj_costs)     # 7x2 model: finding 6
+        assert np.max(np.abs(q.x[b].cpu().numpy() - np.asarray(o.x))) <= 1e-5 * np.max(np.abs(np.asarray(o.x)))
+
+
+@pytest.mark.gpu
+def test_lateral_solution_back_to_cartesian_and_resampled(prep_lib, solver_libs):
+    """Row f3, second half (path_optim.py:303-307): after the lateral solve the Frenet offsets move the
+    reference line to the planned path, which is resampled for the velocity planner — chained on
+    the device behind the corridor shaping (row f2) and the solve, against numpy + the oracle."""
+    from tpl_b200 import scenarios as sc
+    from tpl_b200.batched import BatchedOptim
+    B, N = 32, 200
+    pb = sc.lateral(batch=B, horizon=N, max_iterations=5, forced=False, seed0=8100)
+    q = sc.apply_to_batched(BatchedOptim(solver_libs[pb.model], batch=B, horizon_max=N), pb)
+    q.update()
+    ref_lines = np.stack([ps.path_case(8100 + b, n=N, ds=0.5, jitter=0.0) for b in range(B)])
+    paths = torch.from_numpy(ref_lines).cuda().contiguous()
+    prep.frenet_to_cartesian(paths, q)
+    rs, ok = prep.resample_path(paths, pb.step, N)
+    assert bool(ok.all())
+    X = q.x.cpu().numpy()
+    for b in (0, 13, 31):
+        p = ref_lines[b].copy()
+        p[:, 0] += -np.sin(p[:, 2]) * X[b, :-1, 0]
+        p[:, 1] += np.cos(p[:, 2]) * X[b, :-1, 0]
+        p[:, 2] += np.arctan(X[b, :-1, 1])
+        np.testing.assert_allclose(paths[b].cpu().numpy(), p, rtol=RTOL, atol=1e-12)
+        want = oprep.resample_path(p, pb.step, N)
+        np.testing.assert_allclose(rs[:, b].t().cpu().numpy(), want, rtol=RTOL, atol=1e-9)

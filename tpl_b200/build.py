@@ -148,13 +148,15 @@ def build_prep(force=False, verbose=False) -> str:
     for fn in (os.path.join(CSRC, "prep.cu"), os.path.join(PKG, "..", "include", "tplb200_prep.h")):
         with open(fn, "rb") as fd:
             h.update(fd.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update((" ".join(NVCC_FLAGS) + " -fmad=false").encode())
     stamp, stamp_file = h.hexdigest(), lib_path + ".stamp"
     if not force and os.path.exists(lib_path) and os.path.exists(stamp_file):
         with open(stamp_file) as fd:
             if fd.read().strip() == stamp:
                 return lib_path
-    cmd = [nvcc_path(), *NVCC_FLAGS, os.path.join(CSRC, "prep.cu"), "-o", lib_path]
+    # -fmad=false: the preparation kernels keep the reference's operation order (decisions on
+    # sample intervals, tolerances of the resampling march) and are nowhere near FP64 bound
+    cmd = [nvcc_path(), *NVCC_FLAGS, "-fmad=false", os.path.join(CSRC, "prep.cu"), "-o", lib_path]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -27,9 +27,12 @@ import torch
 
 _D = C.c_void_p
 EXPORTS = ("tplb_prep_abi_version", "tplb_prep_last_error", "tplb_rampify_velocity", "tplb_rampify_lateral",
-           "tplb_shift_interp", "tplb_update_ego")
+           "tplb_shift_interp", "tplb_update_ego", "tplb_project", "tplb_resample_scratch_doubles",
+           "tplb_resample_path", "tplb_frenet_to_cartesian")
+PROJECTION_FIELDS = ("distance", "arc_len", "alpha", "index", "start", "end", "point_x", "point_y",
+                     "tangent_x", "tangent_y", "angle", "in_bounds")
 KINDS = {"linear": 0, "zero": 1}
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class PrepError(RuntimeError):
@@ -61,6 +64,15 @@ def load(path=None):
     lib.tplb_rampify_lateral.restype = C.c_int32
     lib.tplb_shift_interp.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_double, _D, C.c_int32, _D, _D, C.c_void_p]
     lib.tplb_shift_interp.restype = C.c_int32
+    lib.tplb_project.argtypes = [C.c_int32, C.c_int32, C.c_int32, _D, _D, C.c_int32, _D, C.c_void_p]
+    lib.tplb_project.restype = C.c_int32
+    lib.tplb_resample_scratch_doubles.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    lib.tplb_resample_scratch_doubles.restype = C.c_size_t
+    lib.tplb_resample_path.argtypes = [C.c_int32, C.c_int32, _D, C.c_double, C.c_int32, _D, C.c_int32, C.c_int32,
+                                       _D, _D, _D, C.c_void_p]
+    lib.tplb_resample_path.restype = C.c_int32
+    lib.tplb_frenet_to_cartesian.argtypes = [C.c_int32, C.c_int32, C.c_int32, _D, _D, C.c_void_p]
+    lib.tplb_frenet_to_cartesian.restype = C.c_int32
     if lib.tplb_prep_abi_version() != ABI_VERSION:
         raise PrepError(f"{path}: ABI version {lib.tplb_prep_abi_version()} != {ABI_VERSION}")
     _LIB = lib
@@ -165,3 +177,80 @@ def shift_interp(arr, step, arc_len, kind="linear", device=None):
         raise ValueError(f'Expected "arr" with shape (B, n) or (B, n, rows), but found {tuple(t.shape)}')
     out = shift_interp_soa(t.permute(1, 2, 0).contiguous(), step, arc_len, kind).permute(2, 0, 1)
     return out.squeeze(-1) if squeeze else out
+
+
+# ---- row f1: reference-path preparation -------------------------------------------------------------
+def _paths(paths, dev, min_cols):
+    t = paths if isinstance(paths, torch.Tensor) else torch.as_tensor(np.asarray(paths, dtype=np.float64))
+    t = t.to(device=dev, dtype=torch.float64, non_blocking=True)
+    if t.ndim == 2:
+        t = t.unsqueeze(0)
+    if t.ndim != 3 or t.shape[2] < min_cols:
+        raise ValueError(f'Expected "path" with shape (B, P, >={min_cols}), but found {tuple(t.shape)}')
+    return t.contiguous()
+
+
+def project(paths, position, closed=False, device=None):
+    """``util.project`` (library/src/utils.cpp:257-408) for B (path, position) pairs: paths (B, P, >=2),
+    position (B, 2) -> dict of (B,) tensors named like the reference's ``Projection`` members
+    (``distance, arc_len, alpha, index, start, end, point_x, ...``); the MPC takes ``x0[5] = arc_len``
+    from it (control/model_predictive_controller.py:188-189)."""
+    lib = load()
+    dev = _device(device)
+    with torch.cuda.device(dev):
+        p = _paths(paths, dev, 2)
+        batch, points, stride = p.shape
+        pos = (position if isinstance(position, torch.Tensor)
+               else torch.as_tensor(np.asarray(position, dtype=np.float64))).to(dev, torch.float64).reshape(-1, 2).contiguous()
+        if pos.shape[0] != batch:
+            raise ValueError(f'Expected "position" with shape ({batch}, 2), but found {tuple(pos.shape)}')
+        out = torch.empty((len(PROJECTION_FIELDS), batch), dtype=torch.float64, device=dev)
+        rc = lib.tplb_project(batch, points, stride, p.data_ptr(), pos.data_ptr(), int(bool(closed)), out.data_ptr(),
+                              torch.cuda.current_stream(dev).cuda_stream)
+        _check(lib, rc, "tplb_project")
+    return dict(zip(PROJECTION_FIELDS, out))
+
+
+def resample_path(paths, step_size, steps, start_index=0, zero_vel_at_end=False, closed=False, device=None):
+    """``util.resample_path`` (library/tpl/util.py:134-191 over tplcpp.resample, library/src/utils.cpp:410-560)
+    for B paths (B, P, 6) of x, y, orientation, s, curvature, velocity -> ``(rs, ok)``:
+    ``rs`` (6, B, steps) — ``rs[0]`` ... ``rs[5]`` are (B, steps) arrays that can be assigned to solver
+    parameters directly (``opt.params.ref_x = rs[0]``); ``rs.permute(1, 2, 0)`` is the reference's
+    (steps, 6) array per problem — and ``ok`` (B,) bool, False where the reference returns None."""
+    lib = load()
+    dev = _device(device)
+    with torch.cuda.device(dev):
+        p = _paths(paths, dev, 6)
+        if p.shape[2] != 6:
+            p = p[:, :, :6].contiguous()
+        batch, points, _ = p.shape
+        start = None
+        if not isinstance(start_index, (int, np.integer)) or int(start_index) != 0:
+            start = torch.as_tensor(np.broadcast_to(np.asarray(start_index), (batch,)).copy(), dtype=torch.int32).to(dev)
+        rs = torch.empty((6, batch, int(steps)), dtype=torch.float64, device=dev)
+        ok = torch.empty(batch, dtype=torch.int32, device=dev)
+        scratch = torch.empty(lib.tplb_resample_scratch_doubles(batch, points, int(steps)), dtype=torch.float64, device=dev)
+        rc = lib.tplb_resample_path(batch, points, p.data_ptr(), float(step_size), int(steps),
+                                    None if start is None else start.data_ptr(), int(bool(zero_vel_at_end)),
+                                    int(bool(closed)), rs.data_ptr(), ok.data_ptr(), scratch.data_ptr(),
+                                    torch.cuda.current_stream(dev).cuda_stream)
+        _check(lib, rc, "tplb_resample_path")
+    return rs, ok.bool()
+
+
+def frenet_to_cartesian(paths, opt):
+    """planning/path_vel_decomp/path_optim.py:303-305 for the whole batch, in place on ``paths`` (B, n, 6)
+    (a contiguous CUDA tensor, n = opt.horizon): the lateral offsets ``opt.x[:, :-1, 0]`` and slopes
+    ``opt.x[:, :-1, 1]`` of the solved lateral problems move the reference line to the planned path."""
+    lib = load()
+    if not (isinstance(paths, torch.Tensor) and paths.is_cuda and paths.is_contiguous() and paths.ndim == 3
+            and paths.shape[2] == 6 and paths.dtype == torch.float64):
+        raise PrepError("frenet_to_cartesian needs a contiguous fp64 CUDA tensor (B, n, 6)")
+    batch, n, _ = paths.shape
+    if batch != opt.batch or n > opt.horizon:
+        raise ValueError(f"paths {tuple(paths.shape)} do not match the solver (batch {opt.batch}, horizon {opt.horizon})")
+    with torch.cuda.device(paths.device):
+        rc = lib.tplb_frenet_to_cartesian(batch, n, opt.X, paths.data_ptr(), opt._x.data_ptr(),
+                                          torch.cuda.current_stream(paths.device).cuda_stream)
+        _check(lib, rc, "tplb_frenet_to_cartesian")
+    return paths

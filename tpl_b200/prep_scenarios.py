@@ -109,3 +109,45 @@ def ego_cases():
     return [ego_case(600), ego_case(601, dt=0.02), ego_case(602, acc_dead_time=0.0, steer_dead_time=0.0),
             ego_case(603, acc_dead_time=0.05, steer_dead_time=0.3, dt=0.01), ego_case(604, steps=150, dt=0.05),
             ego_case(605, v_ch=12.0, max_v=8.0)]
+
+
+# ---- row f1: reference-path preparation (util.resample_path, util.project) -----------------------
+def path_case(seed, n=120, ds=0.7, jitter=0.15, duplicates=False):
+    """A planned trajectory as `ModelPredictiveController.update` receives it
+    (control/model_predictive_controller.py:116-128): columns x, y, orientation, s, curvature,
+    velocity, irregularly spaced along a curvy road (so resampling has real work to do)."""
+    rng = np.random.default_rng(seed)
+    steps = ds * (1.0 + jitter * rng.uniform(-1.0, 1.0, n))
+    s = np.concatenate([[0.0], np.cumsum(steps[:-1])])
+    kappa = 0.03 * np.sin(s / 11.0 + rng.uniform(0.0, 6.0))
+    heading = rng.uniform(-3.0, 3.0) + np.concatenate([[0.0], np.cumsum(kappa[:-1] * steps[:-1])])
+    x = rng.uniform(-5.0, 5.0) + np.concatenate([[0.0], np.cumsum(np.cos(heading[:-1]) * steps[:-1])])
+    y = rng.uniform(-5.0, 5.0) + np.concatenate([[0.0], np.cumsum(np.sin(heading[:-1]) * steps[:-1])])
+    v = 8.0 + 2.0 * np.sin(s / 20.0 + rng.uniform(0.0, 6.0))
+    path = np.stack([x, y, heading, s, kappa, v], axis=1)
+    if duplicates:                                   # repeated points are dropped by resample (utils.cpp:431-437)
+        path = np.insert(path, [10, 10, 55], path[[10, 10, 55]], axis=0)[:n]
+    return path
+
+
+def path_cases():
+    """(path, step_size, steps, start_index, zero_vel_at_end): the MPC call (ref_step, 100 samples, zero
+    velocity at the end), the lateral planner's call (opt.step, horizon), a start inside the path, a
+    request that runs past the end of the path (extrapolation branch, util.py:164-168)."""
+    return [
+        (path_case(1), 0.5, 100, 0, True),
+        (path_case(2), 0.5, 100, 0, False),
+        (path_case(3, n=150), 0.5, 200, 0, False),        # longer than the path: extrapolates
+        (path_case(4), 0.35, 120, 17, True),
+        (path_case(5, n=80, ds=1.1), 1.0, 60, 3, False),
+    ]
+
+
+def path_batch(batch, n=120, seed0=0):
+    """`batch` paths of `n` points, (B, n, 6), plus query positions near them, (B, 2)."""
+    paths = np.stack([path_case(seed0 + b, n=n) for b in range(batch)])
+    rng = np.random.default_rng(seed0 + 12345)
+    k = rng.integers(5, n - 5, batch)
+    off = rng.normal(0.0, 0.6, (batch, 2))
+    pos = paths[np.arange(batch), k, :2] + off
+    return paths, pos
