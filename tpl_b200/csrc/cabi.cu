@@ -312,6 +312,11 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
             if (fused_sweep) {
                 // linearise + Riccati in one pass over the stages; installs the step the previous
                 // line search accepted on the way (no accept / linearize / record traffic)
+                if (s > 0 && q.keep_previous) {
+                    prof.before();
+                    tplb::keep_previous_kernel<Model><<<dim3(sgx, T + 1), sb, 0, st>>>(q, ws);
+                    prof.after(TPLB_K_ACCEPT);
+                }
                 prof.before();
                 if (s == 0) tplb::sweep_kernel<Model, R, false><<<pgrid, pb, 0, st>>>(q, ws, s);
                 else tplb::sweep_kernel<Model, R, true><<<pgrid, pb, 0, st>>>(q, ws, s);

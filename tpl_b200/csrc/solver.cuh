@@ -1020,7 +1020,8 @@ backward_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteratio
 // fused linearise + Riccati sweep — the throughput sequence's replacement for
 // accept_kernel + linearize_kernel + backward_kernel.  Thread per problem, t = T-1 .. 0:
 //   * the trajectory is read straight from the candidate the previous line search accepted
-//     (ws.winner) and installed into x, u on the way (optim.c:844-848) — no separate copy pass;
+//     (ws.winner) and installed into x, u on the way (optim.c:844-848) — no separate copy pass
+//     (q.keep_previous: keep_previous_kernel saves x, k of the winners in front of the sweep);
 //   * the derivative record of stage t is evaluated in registers and consumed by the Riccati
 //     step of the same stage (optim.c:896-985) — it never travels through HBM
 //     (q.keep_records != 0: it is also stored for the fx..lux views);
@@ -1059,7 +1060,6 @@ __device__ __forceinline__ void dev_sweep(const tplb_batch& q, const Workspace& 
     const S* cu = scratch<S>(ws.cand_u) + (size_t)(install ? win : 0) * q.t_max * U * B + b;
     double* qx = q.x + b;
     double* qu = q.u + b;
-    const bool keep = install && q.keep_previous != 0;
 
     // component i of stage t of the trajectory this iteration linearises about
     auto load_x = [&](int t, int i) -> R {
@@ -1078,7 +1078,6 @@ __device__ __forceinline__ void dev_sweep(const tplb_batch& q, const Workspace& 
 #pragma unroll
         for (int i = 0; i < X; ++i) {
             const size_t idx = ((size_t)t * X + i) * B;
-            if (keep) q.prev_x[idx + b] = qx[idx];
             qx[idx] = (double)x[i];
         }
     };
@@ -1087,7 +1086,6 @@ __device__ __forceinline__ void dev_sweep(const tplb_batch& q, const Workspace& 
 #pragma unroll
         for (int d = 0; d < U; ++d) {
             const size_t idx = ((size_t)t * U + d) * B;
-            if (keep) q.prev_k[idx + b] = q.k[idx + b];
             qu[idx] = (double)u[d];
         }
     };
@@ -1158,7 +1156,7 @@ __device__ __forceinline__ void dev_sweep(const tplb_batch& q, const Workspace& 
         load_stage_consts<M, R>(q, ws, scene, t, sc);
         if (t > 0) fetch(t - 1);
         install_x(t, x);
-        install_u(t, u);                         // (reads the previous gains before they are overwritten)
+        install_u(t, u);
 
         R rec[NC];
         stage_record<M, R>(P, x, u, lam, w, sc, R(t), dt, rec);
@@ -1178,6 +1176,31 @@ __device__ __forceinline__ void dev_sweep(const tplb_batch& q, const Workspace& 
         }
     }
     if (q.keep_records && b == 0) *ws.records_f32 = sizeof(SR) == sizeof(float);
+}
+
+// prev_x <- x, prev_k <- k for the problems whose last line search accepted a step (optim.c:844-845),
+// in front of a sweep that is about to install that step and overwrite the gains.  Stage parallel;
+// launched only when the caller wants prev_x / prev_k maintained (q.keep_previous).
+template <typename M>
+__global__ void keep_previous_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
+    using D = Dims<M>;
+    constexpr int X = D::X, U = D::U;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y, B = q.batch;
+    if (b >= B || ws.winner[b] < 0) return;
+    const int T = horizon_of(q, b);
+    if (t > T) return;
+#pragma unroll
+    for (int i = 0; i < X; ++i) {
+        const size_t idx = ((size_t)t * X + i) * B + b;
+        q.prev_x[idx] = q.x[idx];
+    }
+    if (t < T) {
+#pragma unroll
+        for (int d = 0; d < U; ++d) {
+            const size_t idx = ((size_t)t * U + d) * B + b;
+            q.prev_k[idx] = q.k[idx];
+        }
+    }
 }
 
 template <typename M, typename R, bool kAccept>
