@@ -639,11 +639,26 @@ def test_single_launch_agrees_with_the_launch_sequence(model, kw, tol, solver_li
             assert err <= tol, (n, err)
 
 
-def test_edge_shapes(solver_libs, oracle_libs, cpu_solver):
+@pytest.mark.parametrize("rounds", [0, "auto"])
+def test_edge_shapes(rounds, solver_libs, oracle_libs, cpu_solver):
     """Shortest and longest horizons (optim.c:1726-1734: 1..299), a batch that is not a
     multiple of the warp size, an EMPTY parameter array (lookups return 0.0, optim.c:363-365,
-    380-382) and a one-sample array."""
+    380-382) and a one-sample array — through the batched launch sequence and through the automatic
+    choice (single launch where the problem fits shared memory: T = 1, 2, 30; launch sequence for T = 299)."""
     from tpl_b200 import scenarios as sc
+    base_factory = _factory
+
+    def _factory(libs, pb):                              # noqa: F811 - shadows the module helper on purpose
+        make = base_factory(libs, pb, 0)
+        if rounds == 0:
+            return make
+
+        def auto():
+            o = make()
+            o.single_launch = 0
+            return o
+        return auto
+
     for horizon, batch in ((1, 5), (2, 33), (299, 3)):
         pb = sc.lateral(batch=batch, horizon=max(horizon, 2), max_iterations=4, forced=True, seed0=31)
         pb.horizon = horizon
