@@ -646,9 +646,9 @@ def test_edge_shapes(rounds, solver_libs, oracle_libs, cpu_solver):
     380-382) and a one-sample array — through the batched launch sequence and through the automatic
     choice (single launch where the problem fits shared memory: T = 1, 2, 30; launch sequence for T = 299)."""
     from tpl_b200 import scenarios as sc
-    base_factory = _factory
+    base_factory = globals()["_factory"]
 
-    def _factory(libs, pb):                              # noqa: F811 - shadows the module helper on purpose
+    def _factory(libs, pb):                              # shadows the module helper inside this test
         make = base_factory(libs, pb, 0)
         if rounds == 0:
             return make
