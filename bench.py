@@ -78,7 +78,7 @@ def hbm_peak_gbs():
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=192)
+    ap.add_argument("--steps", type=int, default=384)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="problems per GPU")
@@ -113,7 +113,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "20"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -327,7 +327,7 @@ def run_ours(a):
 
     def timed(step, clk=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for _ in range(max(a.warmup, depth)):
+        for _ in range(max(a.warmup, 2 * depth)):
             step()
         final_gather()                                   # warm-up of the collective too (NCCL connects lazily)
         pipe.join()
@@ -514,7 +514,7 @@ def run_ours(a):
                 "cuda_graph_per_slot": not a.no_graph,
                 "line_search_rounds": a.line_search_rounds,
                 "keep_previous": False, "keep_records": False,
-                "timed_region": f"{a.steps} steps after {max(a.warmup, depth)} warm-up steps; includes filling and "
+                "timed_region": f"{a.steps} steps after {max(a.warmup, 2 * depth)} warm-up steps; includes filling and "
                                 f"draining the {depth} streams",
                 "flush": "working set per step (candidates, gains, trajectories: "
                          f"{opt._workspace_bytes / 1e6:.0f} MB per batch, {depth} batches in flight) exceeds "
