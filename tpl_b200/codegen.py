@@ -224,6 +224,38 @@ def _pair_sincos(exprs):
     return [e.xreplace(repl) for e in exprs], [a.xreplace(repl) for a in args]
 
 
+def _expand_trig_of_known_angles(exprs):
+    """CUDA dialect: ``sin / cos(A +- B)`` by the angle-addition formulas when the sine or cosine of A
+    and of B are evaluated in the same routine anyway.  The path-relative bicycle model takes
+    ``cos(ref_phi(s) - phi)`` next to ``sincos(ref_phi(s))`` and ``sincos(phi)``: evaluated literally
+    the third call waits for the lookup AND runs a full argument reduction + polynomial inside the
+    rollout's dependent chain; as ``cos A cos B + sin A sin B`` it is two FMAs on values that exist
+    already.  Mathematically identical, absolute rounding error of the same size."""
+    known = set()
+    for e in exprs:
+        for f in e.atoms(sp.sin, sp.cos):
+            known.add(f.args[0])
+
+    def signed(term):
+        if isinstance(term, sp.Mul) and term.args[0] == -1:
+            return -1, sp.Mul(*term.args[1:])
+        return 1, term
+
+    def rewrite(f):
+        arg = f.args[0]
+        if not isinstance(arg, sp.Add) or len(arg.args) != 2:
+            return f
+        (sa, a), (sb, b) = signed(arg.args[0]), signed(arg.args[1])
+        if a not in known or b not in known or a.is_number or b.is_number:
+            return f
+        sin_a, sin_b = sa * sp.sin(a), sb * sp.sin(b)
+        if isinstance(f, sp.cos):
+            return sp.cos(a) * sp.cos(b) - sin_a * sin_b
+        return sin_a * sp.cos(b) + sp.cos(a) * sin_b
+
+    return [e.replace(lambda x: isinstance(x, (sp.sin, sp.cos)), rewrite) for e in exprs]
+
+
 def print_body(printer: ModelPrinter, outputs: Sequence[Tuple[str, sp.MatrixBase]],
                indent="    ") -> str:
     """One CSE pass over all ``outputs`` and the statements that evaluate them."""
@@ -236,6 +268,7 @@ def print_body(printer: ModelPrinter, outputs: Sequence[Tuple[str, sp.MatrixBase
     printer.used_scalars = set()
     pair_args = []
     if printer.dialect.name == "cuda":
+        flat = _expand_trig_of_known_angles(flat)
         flat, pair_args = _pair_sincos(flat)
     n_out = len(flat)
     if flat:

@@ -19,6 +19,7 @@ __device__ __forceinline__ void m_sincos(double x, double* s, double* c) { sinco
 __device__ __forceinline__ double m_sqrt(double x) { return sqrt(x); }
 __device__ __forceinline__ double m_rsqrt(double x) { return rsqrt(x); }
 __device__ __forceinline__ double m_inv(double x) { return 1.0 / x; }
+__device__ __forceinline__ double m_div(double a, double b) { return a / b; }
 #else
 __device__ __forceinline__ double m_sin(double x) { return sin_bf(x); }
 __device__ __forceinline__ double m_cos(double x) { return cos_bf(x); }
@@ -27,6 +28,11 @@ __device__ __forceinline__ void m_sincos(double x, double* s, double* c) { sinco
 __device__ __forceinline__ double m_sqrt(double x) { return sqrt_bf(x); }
 __device__ __forceinline__ double m_rsqrt(double x) { return rsqrt_bf(x); }
 __device__ __forceinline__ double m_inv(double x) { return inv_bf(x); }
+// a / b of the interpolation lookups: reciprocal (correctly rounded on every argument tried, loop
+// invariant for a constant grid step) + one exact-remainder correction — Markstein's sequence,
+// which returns the correctly rounded quotient and therefore the same sample interval as the
+// reference's division, without the slow-path branch of the built-in operator
+__device__ __forceinline__ double m_div(double a, double b) { return div_bf(a, b); }
 #endif
 // fp32 compute mode: libdevice's single-precision functions (<= 2 ulp, no slow path below 1e5)
 __device__ __forceinline__ float m_sin(float x) { return sinf(x); }
@@ -36,6 +42,7 @@ __device__ __forceinline__ void m_sincos(float x, float* s, float* c) { sincosf(
 __device__ __forceinline__ float m_sqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ float m_rsqrt(float x) { return rsqrtf(x); }
 __device__ __forceinline__ float m_inv(float x) { return 1.0f / x; }
+__device__ __forceinline__ float m_div(float a, float b) { return a / b; }
 
 template <typename R> __device__ __forceinline__ R sq(R a) { return a * a; }
 template <typename R> __device__ __forceinline__ R pow3h(R a) { return a * m_sqrt(a); }
@@ -51,9 +58,8 @@ template <typename R> __device__ __forceinline__ R ipow8(R a) { R b = a * a; b =
 // min() picks size-1; CUDA's conversion would saturate to 0, hence explicit.
 template <typename R>
 __device__ __forceinline__ int sample_index(R v, int n) {
-    if (!(v >= R(0))) return n - 1;
-    if (v >= R(n)) return n - 1;
-    return static_cast<int>(v);
+    const bool outside = !(v >= R(0)) || v >= R(n);          // NaN and negative positions select the last sample
+    return outside ? n - 1 : static_cast<int>(v);
 }
 
 // fmod(a, b) for b > 0: |a| < b returns a itself (what fmod returns, exactly); libdevice's general
@@ -81,47 +87,52 @@ __device__ __forceinline__ R sample_at(const double* p) {
     else return R(*p);
 }
 
+// The lookups are branch-free (an empty row gives 0.0 through a select, optim.c:363-365, 380-382):
+// inside the rollout chain every branch ends a basic block and with it the overlap of independent work.
+template <typename R, bool kGlobal>
+__device__ __forceinline__ R sample_or_zero(const double* p, int i, int n) {
+    return n > 0 ? sample_at<R, kGlobal>(p + (i > 0 ? i : 0)) : R(0);
+}
+
 // optim.c:374-388 (+ initInterp :347-355)
 template <typename R, bool kGlobal>
 __device__ __forceinline__ R row_lerp(const double* p, int n, R x0, R dx, R x) {
-    if (n == 0) return R(0);
-    const R q = (x - x0) / dx;
+    const R q = m_div(x - x0, dx);
     const int lo = sample_index(floor(q), n);
     const int hi = sample_index(ceil(q), n);
     R w = q - R(lo);
     w = (R(0) > w) ? R(0) : w;
     w = (w < R(1)) ? w : R(1);
-    return (R(1) - w) * sample_at<R, kGlobal>(p + lo) + w * sample_at<R, kGlobal>(p + hi);
+    const R v = (R(1) - w) * sample_or_zero<R, kGlobal>(p, lo, n) + w * sample_or_zero<R, kGlobal>(p, hi, n);
+    return n > 0 ? v : R(0);
 }
 
 // optim.c:392-406
 template <typename R, bool kGlobal>
 __device__ __forceinline__ R row_lerp_angle(const double* p, int n, R x0, R dx, R x) {
-    if (n == 0) return R(0);
-    const R q = (x - x0) / dx;
+    const R q = m_div(x - x0, dx);
     const int lo = sample_index(floor(q), n);
     const int hi = sample_index(ceil(q), n);
     R w = q - R(lo);
     w = (R(0) > w) ? R(0) : w;
     w = (w < R(1)) ? w : R(1);
-    const R v0 = sample_at<R, kGlobal>(p + lo);
-    return v0 + short_angle_dist(v0, sample_at<R, kGlobal>(p + hi)) * w;
+    const R v0 = sample_or_zero<R, kGlobal>(p, lo, n);
+    const R v = v0 + short_angle_dist(v0, sample_or_zero<R, kGlobal>(p, hi, n)) * w;
+    return n > 0 ? v : R(0);
 }
 
 // optim.c:357-370
 template <typename R, bool kGlobal>
 __device__ __forceinline__ R row_box_interp(const double* p, int n, R dx, R x) {
-    if (n == 0) return R(0);
-    return sample_at<R, kGlobal>(p + sample_index(floor(x / dx), n));
+    return sample_or_zero<R, kGlobal>(p, sample_index(floor(m_div(x, dx)), n), n);
 }
 
 // optim.c:330 — the reference indexes unchecked; clamp instead of reading out of bounds
 template <typename R, bool kGlobal>
 __device__ __forceinline__ R row_value(const double* p, int n, R i) {
-    if (n == 0) return R(0);
     int j = static_cast<int>(i);
     j = j < 0 ? 0 : (j >= n ? n - 1 : j);
-    return sample_at<R, kGlobal>(p + j);
+    return sample_or_zero<R, kGlobal>(p, j, n);
 }
 
 // Parameter view of ONE problem: scalars of its scene and its scene's rows of the
