@@ -734,14 +734,15 @@ __global__ void expand_derivatives_kernel(const __grid_constant__ tplb_batch q, 
 template <int U, typename R>
 __device__ __forceinline__ void gain_inverse(const R (&Quu)[U][U], R mu, R (&Mi)[U][U]) {
     static_assert(U == 1 || U == 2, "more than two controls are not supported (genopt.py:420-425)");
+    // -1 / x as the negated straight-line reciprocal (correctly rounded on every argument tried, so the
+    // value of the reference's division; no slow-path call in the middle of the Riccati step)
     if constexpr (U == 1) {
-        R s = R(0);
-        if (Quu[0][0] > R(0)) s = R(-1) / (Quu[0][0] + mu);     // test on the un-regularised value
+        const R s = (Quu[0][0] > R(0)) ? -m_inv(Quu[0][0] + mu) : R(0);     // test on the un-regularised value
         Mi[0][0] = s;
     } else {
         const R a = Quu[0][0] + mu, bb = Quu[0][1], d = Quu[1][1] + mu;
         const R det = a * d - bb * bb;
-        const R s = R(-1) / det;                          // no definiteness check
+        const R s = -m_inv(det);                          // no definiteness check
         Mi[0][0] = d * s;
         Mi[0][1] = -bb * s;
         Mi[1][0] = Mi[0][1];
@@ -889,20 +890,16 @@ __device__ __forceinline__ void riccati_stage(const R (&rec)[Dims<M>::COMPACT], 
 
     control_gains<X, U, R>(Quu, Qu, Qux, mu, k, K);
 
-    // box limits on the feed-forward step (optim.c:950-963)
+    // box limits on the feed-forward step (optim.c:950-963): two independent tests on u + k, the
+    // lower one wins if both fire; selects instead of branches keep the step one basic block
 #pragma unroll
     for (int d = 0; d < U; ++d) {
         const R cand = ub[d] + k[d];
-        if (cand > hib[d]) {
-            k[d] = hib[d] - ub[d];
+        const bool above = cand > hib[d], below = cand < lob[d];
+        k[d] = above ? hib[d] - ub[d] : k[d];
+        k[d] = below ? lob[d] - ub[d] : k[d];
 #pragma unroll
-            for (int j = 0; j < X; ++j) K[d][j] = R(0);
-        }
-        if (cand < lob[d]) {
-            k[d] = lob[d] - ub[d];
-#pragma unroll
-            for (int j = 0; j < X; ++j) K[d][j] = R(0);
-        }
+        for (int j = 0; j < X; ++j) K[d][j] = (above || below) ? R(0) : K[d][j];
     }
 
     // value function (optim.c:965-984)
@@ -1128,33 +1125,29 @@ __device__ __forceinline__ void dev_sweep(const tplb_batch& q, const Workspace& 
         M::end_derivatives(P, xT, sc, R(T), dt, Vx, &Vxx[0][0]);
     }
 
-    // the trajectory of stage t is fetched one stage ahead (HBM latency); the stage constants (one
-    // set per scene, L1/L2 resident) and the multipliers are read where the stage starts
-    R nx[X], nu[U], nhi[U], nlo[U];
+    // Software pipeline: the inputs of stage t-1 (trajectory, box limits, multipliers, stage constants)
+    // are requested right after the derivative record of stage t has consumed the registers that
+    // hold stage t's, i.e. in front of the long Riccati step that does not need them — their HBM /
+    // L2 latency hides behind it and no prefetch register is live during the linearisation.
+    R x[X], u[U], hi[U], lo[U], lam[D::Cs], sc[D::NSCs];
     auto fetch = [&](int t) {
 #pragma unroll
-        for (int i = 0; i < X; ++i) nx[i] = load_x(t, i);
+        for (int i = 0; i < X; ++i) x[i] = load_x(t, i);
 #pragma unroll
         for (int d = 0; d < U; ++d) {
             const size_t idx = ((size_t)t * U + d) * B + b;
-            nu[d] = load_u(t, d);
-            nhi[d] = R(q.u_max[idx]);
-            nlo[d] = R(q.u_min[idx]);
+            u[d] = load_u(t, d);
+            hi[d] = R(q.u_max[idx]);
+            lo[d] = R(q.u_min[idx]);
         }
-    };
-    fetch(T - 1);
-
-    for (int t = T - 1; t >= 0; --t) {
-        R x[X], u[U], hi[U], lo[U], lam[D::Cs], sc[D::NSCs];
-#pragma unroll
-        for (int i = 0; i < X; ++i) x[i] = nx[i];
-#pragma unroll
-        for (int d = 0; d < U; ++d) { u[d] = nu[d]; hi[d] = nhi[d]; lo[d] = nlo[d]; }
 #pragma unroll
         for (int c = 0; c < C; ++c)
             lam[c] = lam_is_zero ? R(0) : R(q.lagrange_multiplier[((size_t)t * C + c) * B + b]);
         load_stage_consts<M, R>(q, ws, scene, t, sc);
-        if (t > 0) fetch(t - 1);
+    };
+    fetch(T - 1);
+
+    for (int t = T - 1; t >= 0; --t) {
         install_x(t, x);
         install_u(t, u);
 
@@ -1165,9 +1158,13 @@ __device__ __forceinline__ void dev_sweep(const tplb_batch& q, const Workspace& 
 #pragma unroll
             for (int s = 0; s < M::DERIV_COMPACT; ++s) __stcs(out + (size_t)s * B, (SR)rec[s]);
         }
+        R ub[U], hib[U], lob[U];
+#pragma unroll
+        for (int d = 0; d < U; ++d) { ub[d] = u[d]; hib[d] = hi[d]; lob[d] = lo[d]; }
+        if (t > 0) fetch(t - 1);
 
         R k[U], K[U][X];
-        riccati_stage<M, R>(rec, Vx, Vxx, mu, u, hi, lo, k, K);
+        riccati_stage<M, R>(rec, Vx, Vxx, mu, ub, hib, lob, k, K);
 #pragma unroll
         for (int d = 0; d < U; ++d) {
             q.k[((size_t)t * U + d) * B + b] = k[d];
