@@ -318,8 +318,7 @@ int run_update_as(const tplb_batch* qp, void* stream_, Profiler& prof) {
                     prof.after(TPLB_K_ACCEPT);
                 }
                 prof.before();
-                if (s == 0) tplb::sweep_kernel<Model, R, false><<<pgrid, pb, 0, st>>>(q, ws, s);
-                else tplb::sweep_kernel<Model, R, true><<<pgrid, pb, 0, st>>>(q, ws, s);
+                tplb::sweep_kernel<Model, R><<<pgrid, pb, 0, st>>>(q, ws, s);
                 prof.after(TPLB_K_BACKWARD);
             } else {
                 prof.before();

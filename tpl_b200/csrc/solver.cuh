@@ -580,6 +580,7 @@ __device__ __forceinline__ void dev_multiplier(const tplb_batch& q, const Worksp
         q.improved[b] = 0;
         q.iterations[b] = 0;
         ws.running[b] = 1;
+        ws.winner[b] = -1;                      // nothing to install in front of the first sweep
         bool zero = C > 0;
 #pragma unroll
         for (int c = 0; c < C; ++c) zero = zero && q.lg_mult_limit[(size_t)c * B + b] == 0.0;
@@ -1025,7 +1026,7 @@ backward_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteratio
 //   * gains K, k are the only per-stage output.
 // Per (problem, stage): x, u (8) + box limits (4) [+ multipliers] in, x, u (8) + K, k (14) out,
 // instead of 32 (accept) + 37 (linearize) + 49 (backward) doubles.
-// kAccept == false: first iteration of an inner loop (nothing to install).
+// In the first iteration of an inner loop ws.winner is -1 (multiplier_kernel): nothing to install.
 // A problem that stopped in the previous iteration only installs its last accepted step.
 // Linearising again after a failed line search (trajectory_changed == 0, optim.c:896 skips
 // it) reproduces the stored record bit for bit: same inputs, same code.
@@ -1042,14 +1043,14 @@ __device__ __forceinline__ void stage_record(const PV& P, const R* x, const R* u
         if (M::deriv_owner(e)) rec[M::deriv_slot(e)] = blk[e];
 }
 
-template <typename M, typename R, bool kAccept>
+template <typename M, typename R>
 __device__ __forceinline__ void dev_sweep(const tplb_batch& q, const Workspace& ws, int b, int iteration) {
     using D = Dims<M>;
     using S = double;                            // line-search candidates are fp64 in every mode
     using SR = scratch_t<R>;                     // derivative records: storage type of the compute precision
     constexpr int X = D::X, U = D::U, C = D::C, NC = D::COMPACT, NSC = D::NSC;
     const int B = q.batch, T = horizon_of(q, b);
-    const int win = kAccept ? ws.winner[b] : -1;
+    const int win = ws.winner[b];
     const bool run = ws.running[b] != 0;
     if (!run && win < 0) return;
     const bool install = win >= 0;
@@ -1200,13 +1201,13 @@ __global__ void keep_previous_kernel(const __grid_constant__ tplb_batch q, Works
     }
 }
 
-template <typename M, typename R, bool kAccept>
+template <typename M, typename R>
 __global__ void __launch_bounds__(128)
 sweep_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteration) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b == 0) *ws.pending_count = 0;           // the line search of this iteration starts empty
     if (b >= q.batch) return;
-    dev_sweep<M, R, kAccept>(q, ws, b, iteration);
+    dev_sweep<M, R>(q, ws, b, iteration);
 }
 
 // gradient-only sweep (optim.c:1038-1076): costate recursion, clipped descent direction
