@@ -705,12 +705,21 @@ def config3_multistart(a, world, rank, dev, peak_fp64):
 
     pipe = graph_pipeline(make, depth, body)
     result = {}
+    opt0_dims = (pipe.slots[0].opt.X, pipe.slots[0].opt.U)
+
+    # pinned host buffers for the winners of this rank's scenes: what a multi-start caller downloads
+    win_x = torch.empty((T + 1, opt0_dims[0], mine), dtype=torch.float64).pin_memory()
+    win_u = torch.empty((T, opt0_dims[1], mine), dtype=torch.float64).pin_memory()
 
     def gather():
         mins, args = [], []
         for slot, (lo, hi) in zip(pipe.slots, bounds):
             with slot:
-                mn, am = slot.opt.argmin_groups(per)
+                o = slot.opt
+                mn, am = o.argmin_groups(per)
+                idx = am.clamp(min=0).to(torch.int64)
+                win_x[:, :, lo:hi].copy_(o._x[:T + 1].index_select(2, idx), non_blocking=True)
+                win_u[:, :, lo:hi].copy_(o._u[:T].index_select(2, idx), non_blocking=True)
             torch.cuda.current_stream().wait_stream(slot.stream)
             mins.append(mn); args.append(am.to(torch.int64) + lo * per)
         result["best"] = tdist.gather_best(torch.cat(mins), torch.cat(args).to(torch.int32), p_lo, counts=counts)
@@ -742,6 +751,9 @@ def config3_multistart(a, world, rank, dev, peak_fp64):
            "single_pass_ms": min(one_pass), "single_pass_solves_per_s": scenes * per / (min(one_pass) * 1e-3),
            "sub_batches_in_flight_per_gpu": depth,
            "collective": "one all_gather of (min cost, argmin) per scene after the last step" if world > 1 else "none",
+           "winners_downloaded": {"d2h_bytes_per_pass_per_gpu": (win_x.numel() + win_u.numel()) * 8,
+                                  "what": "x, u of the best start of every scene of this rank, into pinned host "
+                                          "memory inside the timed pass (instead of all 65536 trajectories)"},
            "best_cost_checksum": float(gmin.sum()), "argmin_checksum": int(garg.sum())}
     lin, bwd, roll = (float(c.double().mean()) for c in pipe.slots[0].opt.work_counters())
     out["work_per_solve"] = {"linearisations": lin, "backward_sweeps": bwd, "rollouts": roll}

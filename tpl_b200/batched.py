@@ -691,6 +691,17 @@ class BatchedOptim:
                 self._stream()), "tplb_argmin_groups")
         return mn, am
 
+    def take(self, indices):
+        """Trajectories of the problems ``indices`` (a device index tensor, e.g. the ``arg_min`` of
+        ``argmin_groups``): ``(x (n, T+1, X), u (n, T, U))`` views of freshly gathered buffers in
+        the solver's layout.  A multi-start caller needs only the winners on the host; downloading
+        them instead of the whole batch cuts the device->host traffic by the group size."""
+        self._require_cuda("take()")
+        T = self._T
+        idx = indices.to(device=self.device, dtype=torch.int64)
+        return (self._traj_view(self._x[:T + 1].index_select(2, idx), T + 1, (self.X,)),
+                self._traj_view(self._u[:T].index_select(2, idx), T, (self.U,)))
+
     def measure_fp64_tflops(self, repeats=5):
         self._require_cuda("measure_fp64_tflops()")
         with torch.cuda.device(self.device):
