@@ -725,6 +725,58 @@ def test_batches_in_flight_are_independent(solver_libs):
             assert torch.equal(a, b)
 
 
+def test_graph_replay_with_pinned_mirrors(solver_libs):
+    """What bench.py's end-to-end leg does: every slot of a SolverPipeline records its step — upload
+    from a pinned HostMirror, update(), download into the mirror — once as a CUDA graph and replays
+    it per batch; the host only rewrites the mirror's input buffers in between.  Same results as a
+    direct solve of each batch, and `take()` returns the winners' trajectories."""
+    from tpl_b200 import scenarios as sc
+    from tpl_b200.streaming import SolverPipeline
+    batches = [sc.mpc_time(batch=128, horizon=40, max_iterations=6, forced=True, seed0=2000 * i) for i in range(5)]
+    alone = []
+    for pb in batches:
+        q = sc.apply_to_batched(_factory(solver_libs, pb, 2)(), pb)
+        q.update()
+        torch.cuda.synchronize()
+        alone.append((q.x.cpu(), q.u.cpu(), q.traj_costs.cpu(), q.iterations.cpu()))
+
+    def make():
+        o = sc.apply_to_batched(_factory(solver_libs, batches[0], 2)(), batches[0])
+        o.keep_previous = o.keep_records = False
+        return o
+    pipe = SolverPipeline(make, depth=2)
+    mirrors = [slot.opt.host_mirror() for slot in pipe.slots]
+
+    def step(slot):
+        o, m = slot.opt, mirrors[slot.index]
+        o.upload(m)
+        o.lagrange_multiplier = 0.0; o.mu = 0.0; o.mu_step = 0
+        o.update()
+        o.download(m)
+    for slot in pipe.slots:
+        slot.capture(step)
+    names = pipe.slots[0].opt.params.scalar_names
+    for k, pb in enumerate(batches):
+        slot = pipe.slots[k % 2]
+        slot.wait()                                          # the previous batch of this slot has been read
+        m = mirrors[slot.index]
+        m.x0.copy_(torch.from_numpy(pb.x0))
+        m.u0.copy_(torch.from_numpy(pb.u0.reshape(tuple(m.u0.shape))))
+        m.scalars.copy_(torch.from_numpy(np.stack([np.broadcast_to(pb.scalars[n], (pb.scenes,)) for n in names])))
+        for n, v in pb.arrays.items():
+            m.arrays[n].copy_(torch.from_numpy(v))
+        pipe.next().replay()
+        slot.wait()
+        want = alone[k]
+        assert torch.equal(m.x, want[0]) and torch.equal(m.u, want[1])
+        assert torch.equal(m.traj_costs, want[2]) and torch.equal(m.iterations, want[3])
+    o = pipe.slots[0].opt
+    mn, am = o.argmin_groups(32)
+    wx, wu = o.take(am)
+    assert torch.equal(wx, o.x[am.long()]) and torch.equal(wu, o.u[am.long()])
+    assert torch.equal(mn, o.traj_costs.view(-1, 32).min(dim=1).values)
+
+
 def test_uploads_from_pinned_host_buffers(solver_libs):
     """Setters take host tensors directly (one copy into the solver's buffer, asynchronous for
     pinned memory); `params.set_scalars` moves all scalars at once.  Same solve as the
