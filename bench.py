@@ -75,6 +75,12 @@ def hbm_peak_gbs():
         return 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
 
 
+def workload_name(batch, horizon, iterations):
+    """`config.workload` of both arms (the reference arm times a bounded sample of the same workload)."""
+    return (f"{batch} independent {MODEL} problems per GPU (X=6,U=2,C=4), N={horizon}, "
+            f"{iterations} forced iLQR iterations, HEUN, fp64 (BASELINE.json configs[1])")
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -215,9 +221,8 @@ def run_reference_arm(a):
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * n / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{n}-problem sample per step of: 4096 independent {MODEL} problems, "
-                               f"N={a.horizon}, {a.iterations} forced iLQR iterations, HEUN, fp64",
-                   "flush": "n/a (CPU)"},
+        "config": {"workload": workload_name(a.batch, a.horizon, a.iterations),
+                   "sample_per_step": n, "flush": "n/a (CPU)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{n} problems per step x {a.steps} steps, one Optim object per problem, "
                                    f"{cores} threads, update() only"},
@@ -508,8 +513,7 @@ def run_ours(a):
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"{B} independent {MODEL} problems per GPU (X=6,U=2,C=4), N={T}, "
-                            f"{I} forced iLQR iterations, HEUN, fp64 (BASELINE.json configs[1])",
+                "workload": workload_name(B, T, I),
                 "problems_per_gpu": B, "stages": T, "iterations": I, "batches_in_flight": depth,
                 "cuda_graph_per_slot": not a.no_graph,
                 "line_search_rounds": a.line_search_rounds,
@@ -683,7 +687,8 @@ def config3_multistart(a, world, rank, dev, peak_fp64):
     (s_lo, s_hi), (p_lo, p_hi) = tdist.shard_scenes(scenes, per, rank, world)
     counts = [hi - lo for lo, hi in (tdist.shard_range(scenes, r, world) for r in range(world))]
     mine = s_hi - s_lo
-    depth = max(1, min(4, mine))
+    # sub-batches of at least 8 scenes (8192 problems): smaller ones are latency-bound launches
+    depth = max(1, min(4, mine // 8))
     bounds = [tdist.shard_range(mine, i, depth) for i in range(depth)]          # scenes of each sub-batch
     subs = [sc.mpc_time(batch=(hi - lo) * per, scenes=hi - lo, horizon=T, max_iterations=I, forced=True,
                         seed0=s_lo + lo) for lo, hi in bounds]

@@ -197,3 +197,35 @@ def test_every_slot_is_readable():
     q.prev_u = 1.5                                   # writable like every array attribute
     assert float(q.prev_u.min()) == 1.5
     assert tuple(q[1].next_x.shape) == (T + 1, X) and tuple(q[1].prev_u.shape) == (T, U)
+
+
+def test_trace_analysis_classifies_flips():
+    """tpl_b200.parity.analyse (used by the parity tests and by bench.py's in-run check): agreement is
+    measured up to the first iteration whose decisions differ; that flip is legitimate only when the line
+    search was decided at round-off level, and the costs must stay together afterwards."""
+    from tpl_b200 import parity
+
+    def snap(cost, alpha=1.0, mu_step=0, it=1, x=1.0):
+        return {"x": np.full((3, 2), x), "u": np.full((2, 1), x), "traj_costs": cost, "alpha": alpha,
+                "mu_step": mu_step, "iterations": it, "termination_condition": 1, "improved": 1,
+                "trajectory_changed": 1, "lg_iterations": 1}
+    ref = [snap(10.0, it=0), snap(5.0, it=1), snap(5.0 - 1e-12, alpha=0.1, it=2), snap(5.0 - 2e-12, it=3)]
+    same = [dict(s) for s in ref]
+    r = parity.analyse(same, ref)
+    assert r["flip"] is None and r["worst"] == 0.0
+    # a different step size at iteration 2, where the reference's cost moved by 2e-13 relative: plateau
+    flipped = [dict(s) for s in ref]
+    flipped[2] = snap(5.0 - 1.1e-12, alpha=1.0, it=2, x=1.0 + 1e-6)
+    flipped[3] = snap(5.0 - 2.1e-12, it=3, x=1.0 + 1e-6)
+    r = parity.analyse(flipped, ref)
+    assert r["flip"] == 2 and r["plateau"] and r["worst"] == 0.0 and r["after"] < 1e-12
+    # the same flip while the cost is still falling: not a plateau
+    ref2 = [snap(10.0, it=0), snap(5.0, it=1), snap(4.0, alpha=0.1, it=2)]
+    bad = [dict(s) for s in ref2]
+    bad[2] = snap(4.5, alpha=1.0, it=2)
+    r = parity.analyse(bad, ref2)
+    assert r["flip"] == 2 and not r["plateau"]
+    # a numerical difference before any flip is reported as `worst`
+    off = [dict(s) for s in ref]
+    off[1] = snap(5.0 * (1 + 1e-7), it=1)
+    assert parity.analyse(off, ref)["worst"] > 1e-8
