@@ -44,7 +44,7 @@ extern "C" {
 #define TPLB_API
 #endif
 
-#define TPLB_ABI_VERSION 2
+#define TPLB_ABI_VERSION 3
 #define TPLB_MAX_ARRAYS 16
 #define TPLB_LINE_SEARCH_STEPS 8          /* alpha = 10^-i, i = 0..7, optim.c:861-863 */
 #define TPLB_HORIZON_MAX 299              /* H_MAX - 1, optim.c:49, 1732 */
@@ -75,6 +75,9 @@ typedef struct {
     int32_t off_fx, off_fu, off_lx, off_lu, off_lxx, off_luu, off_lux;   /* offsets in a dense record */
     int32_t deriv_compact;                 /* doubles per stage actually stored by the solver */
     int32_t num_stage_consts;              /* per-(scene, stage) constants hoisted out of the kernels */
+    const int32_t* array_ndim;             /* [num_arrays] 2: read by blerp (optim.c:483), 1: every other lookup */
+    int32_t num_wrap_pairs;                /* lerp_wrap calls (optim.c:450): (xs, arr) array indices, equal lengths */
+    const int32_t* wrap_pairs;             /* [2 * num_wrap_pairs] */
 } tplb_model_info;
 
 /* One batch of B independent problems sharing horizon and solver settings.
@@ -152,7 +155,8 @@ typedef struct {
     const int32_t* scene_index;    /* [B] */
     const double* scalars;         /* [num_scalars][S] */
     const double* arrays[TPLB_MAX_ARRAYS];   /* array a: [S][array_len[a]] row-major */
-    int32_t array_len[TPLB_MAX_ARRAYS];
+    int32_t array_len[TPLB_MAX_ARRAYS];      /* samples per scene; rows * cols of a 2-D array */
+    int32_t array_cols[TPLB_MAX_ARRAYS];     /* DynArray.dims[1] of a 2-D array (row length), 0 for 1-D arrays */
 
     /* scratch owned by the caller, sized by tplb_workspace_bytes():
      *   stage_consts [t_max+1][num_stage_consts][S]  interpolation lookups that depend on the stage only

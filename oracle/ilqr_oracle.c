@@ -29,7 +29,8 @@
 typedef struct {
     double scalar[TPLO_MAX_SCALARS];
     const double* array[TPLO_MAX_ARRAYS];
-    int64_t length[TPLO_MAX_ARRAYS];
+    int64_t length[TPLO_MAX_ARRAYS];        /* dims[0] */
+    int64_t cols[TPLO_MAX_ARRAYS];          /* dims[1] of a 2-D array, 0 otherwise */
 } tplo_params;
 
 /* ------------------------------------------------------------------ helpers used by generated code */
@@ -101,6 +102,45 @@ static double tplo_box_interp(const tplo_params* P, int a, double dx, double x) 
 /* optim.c:330 */
 static double tplo_array_value(const tplo_params* P, int a, double i) {
     return P->array[a][(size_t)i];
+}
+
+/* optim.c:410-448.  The reference leaves the indices unclamped: with gap <= 0 a position at or
+ * beyond the last sample reads past the array.  The restatement clamps to the last sample there. */
+static double tplo_lerp_wrap(const tplo_params* P, int axs, int a, double len, double dx, double x) {
+    const size_t n = (size_t)P->length[a];
+    if (n == 0) return 0.0;
+    const double first = P->array[axs][0];
+    const double last = first + (double)(n - 1) * dx;
+    const double gap = len - (last - first);
+    x = fmod(x - first, len);
+    if (x < 0) x += len;
+    x += first;
+    double w;
+    size_t lo, hi;
+    if (x >= last && gap > 0) {
+        w = (x - last) / gap;
+        lo = n - 1;
+        hi = 0;
+    } else {
+        const double q = (x - first) / dx;
+        lo = tplo_index(floor(q), n);
+        hi = tplo_index(ceil(q), n);
+        w = q - (double)lo;
+    }
+    return (1.0 - w) * P->array[a][lo] + w * P->array[a][hi];
+}
+
+/* optim.c:457-481: rows = dims[0], cols = dims[1], row-major */
+static double tplo_blerp(const tplo_params* P, int a, double x0, double y0, double dx, double dy,
+                         double x, double y) {
+    const size_t rows = (size_t)P->length[a], cols = (size_t)P->cols[a];
+    if (rows == 0 || cols == 0) return 0.0;      /* the reference would index out of bounds */
+    const tplo_cell cx = tplo_locate(x0, dx, x, cols);
+    const tplo_cell cy = tplo_locate(y0, dy, y, rows);
+    const double* v = P->array[a];
+    const double p0 = cy.w_lo * v[cy.lo * cols + cx.lo] + cy.w_hi * v[cy.hi * cols + cx.lo];
+    const double p1 = cy.w_lo * v[cy.lo * cols + cx.hi] + cy.w_hi * v[cy.hi * cols + cx.hi];
+    return cx.w_lo * p0 + cx.w_hi * p1;
 }
 
 #ifndef TPLO_MODEL_HEADER

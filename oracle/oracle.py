@@ -21,7 +21,8 @@ H_MAX = 300                      # optim.c:49
 class _Params(C.Structure):
     _fields_ = [("scalar", C.c_double * MAX_SCALARS),
                 ("array", C.c_void_p * MAX_ARRAYS),
-                ("length", C.c_int64 * MAX_ARRAYS)]
+                ("length", C.c_int64 * MAX_ARRAYS),
+                ("cols", C.c_int64 * MAX_ARRAYS)]
 
 
 _PTRS = ("x u next_x next_u prev_x prev_k fx fu lx lu lxx luu lux g k K "
@@ -107,6 +108,7 @@ class OracleParams:
             i = self._arrays.index(n)
             self._o._c.params.array[i] = a.ctypes.data
             self._o._c.params.length[i] = a.shape[0] if a.ndim else 0
+            self._o._c.params.cols[i] = a.shape[1] if a.ndim == 2 else 0
         else:
             raise AttributeError(n)
 

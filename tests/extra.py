@@ -15,6 +15,7 @@ import numpy as np
 from tpl_b200 import scenarios as sc
 
 CUSTOM = "custom_unicycle"
+TRACK = "custom_track"
 S_R = (0.25, 0.0, -1e-9, -0.25, 100.0)
 ZOO = (("ref_line_smoother_dk", 120), ("velocity_profile_time", 80))
 STICKY = ((2, 1), (0, 1), (1, 1), (3, 0))      # (max_iterations, max_lg_iterations) of consecutive update() calls
@@ -53,6 +54,59 @@ def configure_custom(o, T, lane):
     for n, v in (("wx", 2.0), ("wu", 0.1), ("r_max", 4.0), ("ref_step", 0.1)):
         setattr(o.params, n, v)
     o.params.lane = lane
+
+
+def track_definition(genopt, spx):
+    """A car on a closed track over a terrain map: the two lookups no shipped problem uses.
+    `lerp_wrap` (optim.c:410-455) gives the track's curvature at the position x (in the dynamics,
+    argument = a state) and the target speed along the lap (in the cost, argument = the stage:
+    a per-stage constant); `blerp` (optim.c:457-486) reads the slope of a 2-D map at (x, y)."""
+    import sympy as sp
+    x, y, phi, v, a, w, t, dt = sp.symbols("x y phi v a w t dt")
+    wy, wv, wu, period, ds, gx0, gy0, gdx, gdy, k_slope = sp.symbols("wy wv wu period ds gx0 gy0 gdx gdy k_slope")
+    track_s, track_k, track_v = (spx.ArraySymbol(n) for n in ("track_s", "track_k", "track_v"))
+    slope = spx.ArraySymbol("slope")
+    v_ref = spx.lerp_wrap(period, ds, 2.0 * t * dt, track_s, track_v)
+    return genopt.Config(
+        [x, y, phi, v], [a, w],
+        {wy: 1.0, wv: 0.5, wu: 0.1, period: 10.5, ds: 0.5, gx0: -5.0, gy0: -3.0, gdx: 2.0, gdy: 0.5, k_slope: 2.0,
+         track_s: None, track_k: None, track_v: None, slope: None},
+        sp.Matrix([v * sp.cos(phi), v * sp.sin(phi),
+                   w + spx.lerp_wrap(period, ds, x, track_s, track_k),
+                   a - k_slope * spx.blerp(gx0, gy0, gdx, gdy, x, y, slope)]),
+        wy * y**2 + wv * (v - v_ref)**2 + wu * (a**2 + w**2),
+        end_costs=5.0 * y**2 + phi**2)
+
+
+TRACK_SCALARS = dict(wy=1.0, wv=0.5, wu=0.1, period=10.5, ds=0.5, gx0=-5.0, gy0=-3.0, gdx=2.0, gdy=0.5, k_slope=2.0)
+TRACK_PICK = (0, 5, 11)
+
+
+def track_inputs():
+    """x0 spread over several laps on both sides of the origin (the wrap, its `x < 0` branch, the
+    closing segment between the last and the first sample) and beyond the map on every side (the
+    clamped cells and the negative-index quirk of initInterp, optim.c:347-355)."""
+    B, T, n = 12, 40, 20
+    rng = np.random.default_rng(21)
+    track_s = 1.0 + 0.5 * np.arange(n)                       # first = 1, last = 10.5, period 10.5: gap = 1
+    track_k = 0.2 * np.sin(2 * np.pi * np.arange(n) / n)[None, :] + rng.normal(0, 0.02, (B, n))
+    track_v = 3.0 + np.cos(2 * np.pi * np.arange(n) / n)[None, :] + rng.normal(0, 0.1, (B, n))
+    slope = 0.3 * rng.normal(0, 1.0, (B, 12, 16)).cumsum(axis=2) / 4.0     # rows (y) x cols (x)
+    x0 = np.stack([np.linspace(-16.0, 27.0, B), rng.normal(0, 0.8, B), rng.normal(0, 0.2, B),
+                   rng.uniform(2.0, 4.0, B)], axis=1)
+    return B, T, track_s, track_k, track_v, slope, x0
+
+
+def configure_track(o, T, track_s, track_k, track_v, slope):
+    o.horizon = T; o.step = 0.1; o.integrator_type = o.HEUN
+    o.max_iterations = 8
+    o.u_min = -3.0; o.u_max = 3.0
+    for n, v in TRACK_SCALARS.items():
+        setattr(o.params, n, v)
+    o.params.track_s = track_s
+    o.params.track_k = track_k
+    o.params.track_v = track_v
+    o.params.slope = slope
 
 
 def zoo_inputs(name, info):
@@ -168,12 +222,21 @@ def run_single(make, zoo_info):
         o.update()
         _final(out, f"custom/{i}", o, T)
         out[f"custom/{i}/lam"] = _a(o.lagrange_multiplier)
+    # ---- user-defined problem with lerp_wrap (dynamics + stage constant) and blerp (2-D map) ----------
+    B, T, track_s, track_k, track_v, slope, x0 = track_inputs()
+    for i in TRACK_PICK:
+        o = make(TRACK)
+        configure_track(o, T, track_s, track_k[i], track_v[i], slope[i])
+        o.x[0] = x0[i]
+        o.update()
+        _final(out, f"track/{i}", o, T)
+        out[f"track/{i}/ctdyn"] = _a(o.ct_dynamics(x0[i], np.array([0.5, -0.1]), 3, 0.1))
     return out
 
 
 def run_batched(make, zoo_info, custom_factory):
     """Same keys from the CUDA solver.  `make(model, batch, horizon_max, scenes=None)` -> BatchedOptim;
-    `custom_factory(batch, horizon_max)` -> BatchedOptim of the user-defined problem."""
+    `custom_factory[name](batch, horizon_max)` -> BatchedOptim of a user-defined problem."""
     import torch
 
     def npy(t):
@@ -243,7 +306,7 @@ def run_batched(make, zoo_info, custom_factory):
             final(out, f"zoo/{name}/{i}", q, i, horizon)
 
     B, T, lanes, x0 = custom_inputs()
-    q = custom_factory(B, T)
+    q = custom_factory[CUSTOM](B, T)
     configure_custom(q, T, lanes)
     q.set_initial_state(x0)
     q.update()
@@ -251,6 +314,17 @@ def run_batched(make, zoo_info, custom_factory):
     for i in (0, 7, 15):
         final(out, f"custom/{i}", q, i, T)
         out[f"custom/{i}/lam"] = npy(q.lagrange_multiplier[i])
+
+    B, T, track_s, track_k, track_v, slope, x0 = track_inputs()
+    q = custom_factory[TRACK](B, T)
+    configure_track(q, T, track_s, track_k, track_v, slope)
+    q.set_initial_state(x0)
+    q.update()
+    c = npy(q.ct_dynamics(x0, np.tile(np.array([0.5, -0.1]), (B, 1)), 3, 0.1))
+    torch.cuda.synchronize()
+    for i in TRACK_PICK:
+        final(out, f"track/{i}", q, i, T)
+        out[f"track/{i}/ctdyn"] = c[i]
     return out
 
 
@@ -273,7 +347,7 @@ def compare(got, want, rtol=1e-9):
             continue
         scale = max(np.max(np.abs(w)), 1e-300) if w.size else 1.0
         e = float(np.max(np.abs(g - w)) / scale) if w.size else 0.0
-        if k.startswith("neg/") or k.startswith("dyn/") or k.startswith("ctdyn/"):
+        if k.startswith("neg/") or k.startswith("dyn/") or k.startswith("ctdyn/") or last == "ctdyn":
             lim = 1e-12
         else:
             lim = rtol

@@ -2,7 +2,7 @@
 """Records tests/golden/ref_extra.npz from the REAL reference solvers (oracle/_ref): the cases of
 tests/extra.py (ilr, shift, dynamics / ct_dynamics incl. the negative-index wrap, sticky state,
 ref_line_smoother_dk, velocity_profile_time, a user-defined RK4 + augmented-Lagrangian problem,
-prev_x / prev_k).  Run in the build container after `python oracle/build_ref.py`:
+prev_x / prev_k, a user-defined problem with lerp_wrap and blerp).  Run in the build container after `python oracle/build_ref.py`:
 
     python tests/golden/make_golden_extra.py
 """
@@ -24,6 +24,7 @@ def main():
     genopt, symext, _ = build_ref.reference_modules()
     # the user-defined problem through the reference's own generator
     build_ref.build(extra.CUSTOM, cfg=extra.custom_definition(genopt, symext))
+    build_ref.build(extra.TRACK, cfg=extra.track_definition(genopt, symext))
 
     def make(model):
         flavour = "strict" if model == "trajectory_tracking_mpc" else "fast"

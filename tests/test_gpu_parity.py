@@ -92,7 +92,7 @@ def test_cuda_matches_reference_extra_cases(single_launch, solver_libs, tmp_path
     `shift` (scalar and per-problem amounts), `dynamics` / `ct_dynamics` incl. the negative-index
     wrap, sticky mu / mu_step, prev_x / prev_k, ref_line_smoother_dk, velocity_profile_time and a
     user-defined problem with RK4, two augmented-Lagrangian iterations, an end cost and a lookup
-    array built through `genopt.build`.  single_launch 0 lets small batches take the one-launch
+    array built through `genopt.build`, and one with `lerp_wrap` and `blerp` (a 2-D array parameter).  single_launch 0 lets small batches take the one-launch
     kernel, -1 forces the batched launch sequences."""
     import os
     from tests import extra
@@ -100,6 +100,7 @@ def test_cuda_matches_reference_extra_cases(single_launch, solver_libs, tmp_path
     from tpl_b200.batched import BatchedOptim
     want = dict(np.load(os.path.join(common.GOLDEN_DIR, "ref_extra.npz")))
     Custom = genopt.build(extra.custom_definition(genopt, spx))
+    Track = genopt.build(extra.track_definition(genopt, spx))      # lerp_wrap, blerp (2-D array parameter)
 
     def tune(o):
         o.single_launch = single_launch
@@ -109,7 +110,9 @@ def test_cuda_matches_reference_extra_cases(single_launch, solver_libs, tmp_path
         return tune(BatchedOptim(solver_libs[model], batch=batch, scenes=scenes, horizon_max=horizon_max))
 
     zoo_info = {n: _cabi.model_info(_cabi.load(solver_libs[n])) for n, _ in extra.ZOO}
-    got = extra.run_batched(make, zoo_info, lambda batch, horizon_max: tune(Custom(batch=batch, horizon_max=horizon_max)))
+    got = extra.run_batched(make, zoo_info, {
+        extra.CUSTOM: lambda batch, horizon_max: tune(Custom(batch=batch, horizon_max=horizon_max)),
+        extra.TRACK: lambda batch, horizon_max: tune(Track(batch=batch, horizon_max=horizon_max))})
     worst, bad = extra.compare(got, want)
     assert not bad, bad[:5]
 

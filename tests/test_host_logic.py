@@ -162,17 +162,41 @@ def test_generated_headers_are_current():
             assert fd.read() == first + "\n// generator sha1: " + gen + "\n" + rest, name
 
 
-def test_unsupported_lookups_are_rejected_at_derive_time():
-    """`blerp` / `lerp_wrap` (optim.c:410-486) have no device implementation: a problem definition
-    using them fails with a clear error when it is derived, not inside nvcc."""
+def test_two_array_and_2d_lookups_host_side():
+    """`lerp_wrap` (two arrays of equal length) and `blerp` (a 2-D array), optim.c:410-486: the
+    generator records how each array parameter is read, the generated code passes the array
+    indices in the reference's argument order, and `params` takes maps as (rows, cols) /
+    (S, rows, cols) and describes them to the C ABI as samples per scene + row length."""
     import sympy as sp
-    from tpl_b200 import derive, genopt, symext as spx
+    from tests import extra
+    from tpl_b200 import codegen, derive, genopt, symext as spx
+    cfg = extra.track_definition(genopt, spx)
+    d = derive.derive(cfg)
+    assert d.array_params == ["track_s", "track_k", "track_v", "slope"]
+    assert codegen.array_shapes(d) == ([1, 1, 1, 2], [(0, 1), (0, 2)])
+    src = codegen.emit_cuda_model(d, "track", cfg.definition_hash())
+    assert "P.lerp_wrap(0, 1, " in src and "P.lerp_wrap(0, 2, " in src and "P.blerp(3, " in src
+    assert "static constexpr int ARRAY_NDIM[4] = {1, 1, 1, 2};" in src
+
     x, u, t, dt = sp.symbols("x u t dt")
-    grid, xs = spx.ArraySymbol("grid"), spx.ArraySymbol("xs")
-    for bad in (spx.blerp(0.0, 0.0, 1.0, 1.0, x, t * dt, grid), spx.lerp_wrap(10.0, 1.0, x, xs, grid)):
-        cfg = genopt.Config([x], [u], [grid, xs], sp.Matrix([u]), (x - bad)**2 + u**2)
-        with pytest.raises(NotImplementedError, match="not supported"):
-            derive.derive(cfg)
+    grid = spx.ArraySymbol("grid")
+    both = genopt.Config([x], [u], [grid], sp.Matrix([u + spx.lerp(0.0, 1.0, x, grid)]),
+                         spx.blerp(0.0, 0.0, 1.0, 1.0, t * dt, 0.0, grid) + u**2)
+    with pytest.raises(ValueError, match="both as a 1-D and as a 2-D"):
+        codegen.array_shapes(derive.derive(both))
+
+    q = genopt.build(cfg)(batch=6, scenes=3, horizon_max=10, device="cpu")
+    q.params.slope = np.arange(12.0).reshape(3, 4)                       # shared by the scenes
+    assert tuple(q.params.slope.shape) == (3, 3, 4)
+    q.params.slope = np.arange(60.0).reshape(3, 4, 5)
+    q.params.track_s = np.arange(7.0)
+    desc = q._descriptor()
+    assert (desc.array_len[3], desc.array_cols[3]) == (20, 5)
+    assert (desc.array_len[0], desc.array_cols[0]) == (7, 0)
+    with pytest.raises(ValueError, match="rows, cols"):
+        q.params.slope = np.arange(5.0)
+    with pytest.raises(ValueError):
+        q.params.track_s = np.zeros((2, 3, 4))
 
 
 def test_every_slot_is_readable():

@@ -37,7 +37,8 @@ def test_golden_default_mode_flags():
 def test_port_matches_reference_extra_cases(oracle_libs, tmp_path):
     """tests/extra.py: `ilr`, `shift`, `dynamics` / `ct_dynamics` (incl. the negative-index wrap),
     sticky state, prev_x / prev_k, the two zoo models without a workload generator and a
-    user-defined RK4 + augmented-Lagrangian + end-cost problem — the C restatement against the
+    user-defined RK4 + augmented-Lagrangian + end-cost problem, a user-defined problem with
+    `lerp_wrap` and `blerp` (2-D array parameter) — the C restatement against the
     vectors recorded from the REAL reference (tests/golden/ref_extra.npz, make_golden_extra.py)."""
     import os
 
@@ -47,11 +48,12 @@ def test_port_matches_reference_extra_cases(oracle_libs, tmp_path):
     from tpl_b200 import _cabi, build, genopt, symext as spx
 
     want = dict(np.load(os.path.join(common.GOLDEN_DIR, "ref_extra.npz")))
-    name, lib = oracle_libs.build_custom(extra.custom_definition(genopt, spx), str(tmp_path))
+    custom = {extra.CUSTOM: oracle_libs.build_custom(extra.custom_definition(genopt, spx), str(tmp_path)),
+              extra.TRACK: oracle_libs.build_custom(extra.track_definition(genopt, spx), str(tmp_path))}
 
     def make(model):
-        if model == extra.CUSTOM:
-            return oracle_libs.OracleOptim(name, lib)
+        if model in custom:
+            return oracle_libs.OracleOptim(*custom[model])
         return oracle_libs.OracleOptim(model)
 
     libs = build.build_zoo([n for n, _ in extra.ZOO])

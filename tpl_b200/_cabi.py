@@ -2,7 +2,7 @@
 
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_ARRAYS = 16
 LINE_SEARCH_STEPS = 8
 HORIZON_MAX = 299
@@ -23,6 +23,7 @@ class ModelInfo(C.Structure):
         ("off_fx", C.c_int32), ("off_fu", C.c_int32), ("off_lx", C.c_int32), ("off_lu", C.c_int32),
         ("off_lxx", C.c_int32), ("off_luu", C.c_int32), ("off_lux", C.c_int32),
         ("deriv_compact", C.c_int32), ("num_stage_consts", C.c_int32),
+        ("array_ndim", C.POINTER(C.c_int32)), ("num_wrap_pairs", C.c_int32), ("wrap_pairs", C.POINTER(C.c_int32)),
     ]
 
 
@@ -44,6 +45,7 @@ class Batch(C.Structure):
         ("trajectory_changed", _D), ("improved", _D), ("termination_condition", _D),
         ("scene_index", _D), ("scalars", _D),
         ("arrays", _D * MAX_ARRAYS), ("array_len", C.c_int32 * MAX_ARRAYS),
+        ("array_cols", C.c_int32 * MAX_ARRAYS),
         ("workspace", _D), ("workspace_bytes", C.c_size_t),
         ("deriv_dense", _D),
         ("horizons", _D),
@@ -111,6 +113,8 @@ def model_info(lib):
         scalar_names=strs(m.scalar_names, m.num_scalars), array_names=strs(m.array_names, m.num_arrays),
         param_order=strs(m.param_order, m.num_params),
         deriv_stride=m.deriv_stride, deriv_compact=m.deriv_compact, num_stage_consts=m.num_stage_consts,
+        array_ndim=[int(m.array_ndim[i]) for i in range(m.num_arrays)],
+        wrap_pairs=[(int(m.wrap_pairs[2 * i]), int(m.wrap_pairs[2 * i + 1])) for i in range(m.num_wrap_pairs)],
         offsets=dict(fx=m.off_fx, fu=m.off_fu, lx=m.off_lx, lu=m.off_lu,
                      lxx=m.off_lxx, luu=m.off_luu, lux=m.off_lux),
     )

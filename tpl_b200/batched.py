@@ -62,7 +62,8 @@ def _fit(value, view):
 class BatchedParams:
     """``opt.params`` (optim.c:1405-1476, genopt.py:321-417): named scalars and
     arrays.  A scalar is one value per scene (assign a float to broadcast); an
-    array is ``(S, L)`` (assign ``(L,)`` to share it between all scenes)."""
+    array is ``(S, L)`` (assign ``(L,)`` to share it between all scenes); an array the problem
+    reads with ``blerp`` is ``(S, rows, cols)`` / ``(rows, cols)``."""
 
     def __init__(self, owner):
         object.__setattr__(self, "_o", owner)
@@ -113,14 +114,16 @@ class BatchedParams:
             o._scalars[o._scalar_index[n]].copy_(_source(v).expand(o.scenes), non_blocking=True)
         elif n in o._array_index:
             t = _source(v)
+            i = o._array_index[n]
+            nd = o._array_ndim[i]                      # 2: a map read by blerp (rows, cols), else 1
             if t.ndim == 0:
                 raise ValueError(f"parameter {n} is an array")
-            if t.ndim == 1:
-                t = t.unsqueeze(0).expand(o.scenes, -1)
-            if t.ndim != 2 or t.shape[0] != o.scenes:
-                raise ValueError(f'Expected "{n}" with shape ({o.scenes}, L) or (L,), but found {tuple(t.shape)}')
-            i = o._array_index[n]
-            if o._arrays[i].shape == t.shape:          # same length: refill the buffer in place
+            if t.ndim == nd:
+                t = t.unsqueeze(0).expand(o.scenes, *t.shape)
+            if t.ndim != nd + 1 or t.shape[0] != o.scenes:
+                dims = "L" if nd == 1 else "rows, cols"
+                raise ValueError(f'Expected "{n}" with shape ({o.scenes}, {dims}) or ({dims}), but found {tuple(t.shape)}')
+            if o._arrays[i].shape == t.shape:          # same shape: refill the buffer in place
                 o._arrays[i].copy_(t, non_blocking=True)
             else:
                 o._arrays[i] = t.to(o.device).contiguous().clone()
@@ -253,7 +256,8 @@ class BatchedOptim:
         self._scalar_index = {n: i for i, n in enumerate(info["scalar_names"])}
         self._array_index = {n: i for i, n in enumerate(info["array_names"])}
         self._scalars = z(max(1, len(self._scalar_index)), S, **f64)
-        self._arrays = [z(S, 0, **f64) for _ in self._array_index]
+        self._array_ndim = list(info["array_ndim"])
+        self._arrays = [z(*((S,) + (0,) * nd), **f64) for nd in self._array_ndim]
         self._horizons = None
         self._workspace = None
         self._deriv_dense = None
@@ -532,7 +536,8 @@ class BatchedOptim:
             setattr(q, name, self._status[name].data_ptr())
         for i, a in enumerate(self._arrays):
             q.arrays[i] = a.data_ptr()
-            q.array_len[i] = a.shape[1]
+            q.array_len[i] = a.numel() // a.shape[0]
+            q.array_cols[i] = a.shape[2] if a.ndim == 3 else 0
         q.workspace = self._workspace.data_ptr()
         q.workspace_bytes = self._workspace_bytes
         q.deriv_dense = self._deriv_dense.data_ptr() if self._deriv_dense is not None else None

@@ -48,8 +48,8 @@ class Dialect:
     real: str
 
 
-CUDA = Dialect("cuda", "R(%s)", "P.%s(%d%s)", "P.scalar(%d)", "R")
-PLAIN_C = Dialect("c", "%s", "tplo_%s(P, %d%s)", "P->scalar[%d]", "double")
+CUDA = Dialect("cuda", "R(%s)", "P.%s(%s%s)", "P.scalar(%d)", "R")
+PLAIN_C = Dialect("c", "%s", "tplo_%s(P, %s%s)", "P->scalar[%d]", "double")
 
 
 class ModelPrinter(C99CodePrinter):
@@ -128,9 +128,9 @@ class ModelPrinter(C99CodePrinter):
             return super()._print_Function(e)
         arrays = [a for a in e.args if isinstance(a, spx.ArraySymbol)]
         others = [a for a in e.args if not isinstance(a, spx.ArraySymbol)]
-        if len(arrays) != 1:
-            raise NotImplementedError(f"{fn} with {len(arrays)} array arguments is not supported")
-        idx = self.array_index[arrays[0].name]
+        if len(arrays) != (2 if fn == "lerp_wrap" else 1):
+            raise NotImplementedError(f"{fn} with {len(arrays)} array arguments")
+        idx = ", ".join(str(self.array_index[a.name]) for a in arrays)      # lerp_wrap: xs, arr (optim.c:450)
         args = "".join(", " + self._print(a) for a in others)
         return self.dialect.opaque_call % (fn, idx, args)
 
@@ -430,6 +430,26 @@ def derivative_layout(r):
     return slots, owner, n, offsets
 
 
+def array_shapes(d: Derivation):
+    """(ndim per array parameter, [(xs, arr) index pairs of lerp_wrap]) as the lookups use them:
+    blerp reads a 2-D array (optim.c:483-486), everything else 1-D; lerp_wrap's two arrays must
+    have the same length (optim.c:450-455).  The host checks bound arrays against this, where
+    the reference's `check()` raises after the solve."""
+    index = {n: i for i, n in enumerate(d.array_params)}
+    ndim = {}
+    pairs = set()
+    for m in d.routines.values():
+        for call in m.atoms(*spx.OPAQUE_FUNCTIONS):
+            arrays = [a for a in call.args if isinstance(a, spx.ArraySymbol)]
+            for a in arrays:
+                want = 2 if isinstance(call, spx.blerp) else 1
+                if ndim.setdefault(a.name, want) != want:
+                    raise ValueError(f"array parameter {a.name} is used both as a 1-D and as a 2-D array")
+            if isinstance(call, spx.lerp_wrap) and len(arrays) == 2:
+                pairs.add((index[arrays[0].name], index[arrays[1].name]))
+    return [ndim.get(n, 1) for n in d.array_params], sorted(pairs)
+
+
 def _count_lookups(m):
     names = {"lerp", "lerp_angle", "lerp_wrap", "box_interp", "blerp", "get_array_value"}
     return len({f for e in _flatten(m) for f in sp.sympify(e).atoms(sp.Function) if type(f).__name__ in names})
@@ -468,6 +488,11 @@ def emit_cuda_model(d: Derivation, name: str, definition_hash: str) -> str:
         body = ", ".join(f'"{s}"' for s in items) if items else '""'
         return f"    static constexpr const char* {tag}[{max(1, len(items))}] = {{{body}}};\n"
 
+    def ints(tag, items):
+        body = ", ".join(str(v) for v in items) if items else "0"
+        return f"    static constexpr int {tag}[{max(1, len(items))}] = {{{body}}};\n"
+
+    ndim, wrap_pairs = array_shapes(d)
     slots, owner, nslots, offsets = derivative_layout(r)
     vxx_kind = entry_kinds(r["endHessian"])
     hoisted_doc = "".join(f"    //   sc[{i}] = {c}\n" for i, c in enumerate(hoisted))
@@ -491,6 +516,10 @@ def emit_cuda_model(d: Derivation, name: str, definition_hash: str) -> str:
         + names("SCALAR_NAMES", d.scalar_params)
         + names("ARRAY_NAMES", d.array_params)
         + names("PARAM_ORDER", d.param_order)
+        + "    // dimensions of every array parameter (2: read by blerp) and the (xs, arr) pairs of lerp_wrap\n"
+        + ints("ARRAY_NDIM", ndim)
+        + f"    static constexpr int NUM_WRAP_PAIRS = {len(wrap_pairs)};\n"
+        + ints("WRAP_PAIRS", [i for p in wrap_pairs for i in p])
         + "\n    // per-(scene, stage) constants: lookups that depend on the stage index only\n"
         + hoisted_doc
         + f"    static constexpr int NUM_STAGE_CONSTS = {len(hoisted)};\n"

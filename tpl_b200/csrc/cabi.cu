@@ -66,6 +66,16 @@ int validate(const tplb_batch* q) {
     if (Model::NUM_SCALARS > 0 && !q->scalars) return fail(TPLB_E_ARG, "scalars is NULL");
     for (int a = 0; a < Model::NUM_ARRAYS; ++a)
         if (q->array_len[a] > 0 && !q->arrays[a]) return fail(TPLB_E_ARG, "a parameter array is NULL");
+    // the reference's check(ARR.ndim == ...) / check(ARR.dims[0] == XS.dims[0]) of the lookups (optim.c:372-486)
+    for (int a = 0; a < Model::NUM_ARRAYS; ++a) {
+        const int cols = q->array_cols[a];
+        if (Model::ARRAY_NDIM[a] == 2 ? (cols <= 0 && q->array_len[a] > 0) || (cols > 0 && q->array_len[a] % cols != 0)
+                                      : cols != 0)
+            return fail(TPLB_E_ARG, "array_cols does not describe the array the problem definition reads (blerp: 2-D, others: 1-D)");
+    }
+    for (int p = 0; p < Model::NUM_WRAP_PAIRS; ++p)
+        if (q->array_len[Model::WRAP_PAIRS[2 * p]] != q->array_len[Model::WRAP_PAIRS[2 * p + 1]])
+            return fail(TPLB_E_ARG, "lerp_wrap: the sample positions and the samples differ in length");
     if (q->keep_previous && (!q->prev_x || !q->prev_k)) return fail(TPLB_E_ARG, "prev_x/prev_k are NULL");
     size_t need = 0;
     tplb::carve<Model>(nullptr, q->batch, q->scenes, q->t_max, &need);
@@ -98,6 +108,7 @@ const tplb_model_info* tplb_model(void) {
         names(Model::ARRAY_NAMES), names(Model::PARAM_ORDER),
         Dm::DENSE, Dm::OFF_FX, Dm::OFF_FU, Dm::OFF_LX, Dm::OFF_LU, Dm::OFF_LXX, Dm::OFF_LUU, Dm::OFF_LUX,
         Model::DERIV_COMPACT, Model::NUM_STAGE_CONSTS,
+        Model::ARRAY_NDIM, Model::NUM_WRAP_PAIRS, Model::WRAP_PAIRS,
     };
     return &info;
 }

@@ -127,6 +127,49 @@ __device__ __forceinline__ R row_box_interp(const double* p, int n, R dx, R x) {
     return sample_or_zero<R, kGlobal>(p, sample_index(floor(m_div(x, dx)), n), n);
 }
 
+// optim.c:410-448: periodic lookup over [xs[0], xs[0] + len); the samples end `gap` before the
+// period does and the last segment blends arr[n-1] back into arr[0].  The reference leaves its
+// indices unclamped (with gap <= 0 a position at or beyond the last sample reads past the
+// array); here they clamp to the last sample.
+template <typename R, bool kGlobal>
+__device__ __forceinline__ R row_lerp_wrap(const double* xs, int nxs, const double* p, int n, R len, R dx, R x) {
+    const R first = sample_or_zero<R, kGlobal>(xs, 0, nxs);
+    const R last = first + R(n - 1) * dx;
+    const R gap = len - (last - first);
+    R y = x - first;
+    y = (fabs(y) < fabs(len)) ? y : fmod(y, len);          // fmod(a, b) = a for |a| < |b|, exactly
+    y = (y < R(0)) ? y + len : y;
+    y += first;
+    const bool across = (y >= last) && (gap > R(0));
+    const R q = m_div(y - first, dx);
+    const int lo = across ? n - 1 : sample_index(floor(q), n);
+    const int hi = across ? 0 : sample_index(ceil(q), n);
+    const R w = across ? m_div(y - last, gap) : q - R(lo);
+    const R v = (R(1) - w) * sample_or_zero<R, kGlobal>(p, lo, n) + w * sample_or_zero<R, kGlobal>(p, hi, n);
+    return n > 0 ? v : R(0);
+}
+
+// optim.c:457-481 (+ initInterp :347-355 per axis): p is rows x cols, row-major; x runs along a row
+template <typename R, bool kGlobal>
+__device__ __forceinline__ R row_blerp(const double* p, int rows, int cols, R x0, R y0, R dx, R dy, R x, R y) {
+    const R qx = m_div(x - x0, dx);
+    const R qy = m_div(y - y0, dy);
+    const int x_lo = sample_index(floor(qx), cols), x_hi = sample_index(ceil(qx), cols);
+    const int y_lo = sample_index(floor(qy), rows), y_hi = sample_index(ceil(qy), rows);
+    R ax = qx - R(x_lo);
+    ax = (R(0) > ax) ? R(0) : ax;
+    ax = (ax < R(1)) ? ax : R(1);
+    R ay = qy - R(y_lo);
+    ay = (R(0) > ay) ? R(0) : ay;
+    ay = (ay < R(1)) ? ay : R(1);
+    const int n = rows * cols;                               // an empty map reads as 0.0 (the reference would index out of bounds)
+    const R p0 = (R(1) - ay) * sample_or_zero<R, kGlobal>(p, y_lo * cols + x_lo, n)
+               + ay * sample_or_zero<R, kGlobal>(p, y_hi * cols + x_lo, n);
+    const R p1 = (R(1) - ay) * sample_or_zero<R, kGlobal>(p, y_lo * cols + x_hi, n)
+               + ay * sample_or_zero<R, kGlobal>(p, y_hi * cols + x_hi, n);
+    return n > 0 ? (R(1) - ax) * p0 + ax * p1 : R(0);
+}
+
 // optim.c:330 — the reference indexes unchecked; clamp instead of reading out of bounds
 template <typename R, bool kGlobal>
 __device__ __forceinline__ R row_value(const double* p, int n, R i) {
@@ -142,7 +185,8 @@ template <typename R>
 struct ParamView {
     const double* scalars;
     const double* const* arrays;
-    const int32_t* len;
+    const int32_t* len;                 // samples per scene (rows * cols of a 2-D array)
+    const int32_t* cols;                // row length of a 2-D array, 0 for a 1-D one
     int32_t num_scenes;
     int32_t scene;
 
@@ -158,6 +202,13 @@ struct ParamView {
     }
     __device__ __forceinline__ R box_interp(int a, R dx, R x) const { return row_box_interp<R, true>(row(a), len[a], dx, x); }
     __device__ __forceinline__ R array_value(int a, R i) const { return row_value<R, true>(row(a), len[a], i); }
+    __device__ __forceinline__ R lerp_wrap(int xs, int a, R period, R dx, R x) const {
+        return row_lerp_wrap<R, true>(row(xs), len[xs], row(a), len[a], period, dx, x);
+    }
+    __device__ __forceinline__ R blerp(int a, R x0, R y0, R dx, R dy, R x, R y) const {
+        const int c = cols[a];
+        return row_blerp<R, true>(row(a), c > 0 ? len[a] / c : 0, c, x0, y0, dx, dy, x, y);
+    }
 };
 
 
@@ -186,6 +237,7 @@ struct StagedParamView {
     R cached[NS > 0 ? NS : 1];
     const double* rows[NA > 0 ? NA : 1];          // shared memory
     int32_t len[NA > 0 ? NA : 1];
+    int32_t cols[NA > 0 ? NA : 1];
 
     __device__ __forceinline__ R scalar(int i) const { return cached[i]; }
     __device__ __forceinline__ R lerp(int a, R x0, R dx, R x) const { return row_lerp<R, false>(rows[a], len[a], x0, dx, x); }
@@ -194,6 +246,13 @@ struct StagedParamView {
     }
     __device__ __forceinline__ R box_interp(int a, R dx, R x) const { return row_box_interp<R, false>(rows[a], len[a], dx, x); }
     __device__ __forceinline__ R array_value(int a, R i) const { return row_value<R, false>(rows[a], len[a], i); }
+    __device__ __forceinline__ R lerp_wrap(int xs, int a, R period, R dx, R x) const {
+        return row_lerp_wrap<R, false>(rows[xs], len[xs], rows[a], len[a], period, dx, x);
+    }
+    __device__ __forceinline__ R blerp(int a, R x0, R y0, R dx, R dy, R x, R y) const {
+        const int c = cols[a];
+        return row_blerp<R, false>(rows[a], c > 0 ? len[a] / c : 0, c, x0, y0, dx, dy, x, y);
+    }
 };
 
 }  // namespace tplb

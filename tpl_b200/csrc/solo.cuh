@@ -363,6 +363,7 @@ solo_update_kernel(const __grid_constant__ tplb_batch q, Workspace ws) {
             for (int i = tid; i < len; i += n) dst[i] = __ldg(src + i);
             P.rows[a] = dst;
             P.len[a] = len;
+            P.cols[a] = q.array_cols[a];
             dst += len;
         }
     }

@@ -145,6 +145,7 @@ __device__ __forceinline__ ParamView<R> param_view_scene(const tplb_batch& q, in
     P.scalars = q.scalars;
     P.arrays = q.arrays;
     P.len = q.array_len;
+    P.cols = q.array_cols;
     P.num_scenes = q.scenes;
     P.scene = scene;
     return P;

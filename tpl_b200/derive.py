@@ -110,17 +110,6 @@ def derive(config) -> Derivation:
     stage_cost = augment_stage_cost(_as_matrix(config.costs), constraints)
     end_cost = _as_matrix(config.end_costs)      # NOT augmented (genopt.py:552)
 
-    # the two lookups no shipped problem uses have no device counterpart: say so here, not in nvcc
-    for name, m in (("dynamics", f), ("costs", stage_cost), ("end_costs", end_cost),
-                    ("constraints", _as_matrix(constraints) if constraints else sp.zeros(0, 1))):
-        for fn in (spx.blerp, spx.lerp_wrap):
-            if m.atoms(fn):
-                raise NotImplementedError(
-                    f"{fn.__name__}() in `{name}`: the B200 solver implements get_array_value, box_interp, lerp and "
-                    f"lerp_angle (optim.c:330-406); {fn.__name__} (optim.c:410-486: "
-                    f"{'2-D arrays' if fn is spx.blerp else 'two array arguments'}) is not supported — "
-                    "no problem definition of the reference uses it")
-
     r = {}
 
     # -- dynamics (genopt.py:93-110)
