@@ -321,9 +321,13 @@ def run_ours(a):
         batch of every rank."""
         if world > 1:
             last = pipe.slots[(pipe._n - 1) % depth]
-            with last:
-                mn, am = last.opt.argmin_groups(group)
-                tdist.gather_best(mn, am, rank * B)
+            # always on the rank's main stream, ordered after the last slot.  Issued from the slot's
+            # own stream, the first collective on EVERY new stream blocked the host for 25-55 ms at
+            # 4 and 8 ranks (NCCL's per-stream set-up), inside the timed region whenever the last
+            # timed step used another slot than the last warm-up step.
+            torch.cuda.current_stream().wait_stream(last.stream)
+            mn, am = last.opt.argmin_groups(group)
+            tdist.gather_best(mn, am, rank * B)
 
     def barrier():
         if world > 1:
@@ -339,14 +343,21 @@ def run_ours(a):
         barrier()
         if clk:
             clk.mark()
+        h0 = time.perf_counter()
         e0.record()
         pipe.fork()
         for _ in range(a.steps):
             step()
+        h1 = time.perf_counter()
         final_gather()
+        h2 = time.perf_counter()
         pipe.join()
         e1.record()
         barrier()
+        if os.environ.get("TPLB_BENCH_DEBUG"):
+            print(f"[rank {rank}] host: enqueue {1e3 * (h1 - h0):.2f} ms, gather call {1e3 * (h2 - h1):.2f} ms, "
+                  f"until idle {1e3 * (time.perf_counter() - h0):.2f} ms; device {e0.elapsed_time(e1):.2f} ms",
+                  file=sys.stderr)
         if clk:
             clk.mark()
         ms = e0.elapsed_time(e1)
@@ -402,6 +413,28 @@ def run_ours(a):
         raise SystemExit(f"end-to-end results differ from the device-resident run: "
                          f"{e2e_cost_check!r} vs {resident_cost_check!r}")
     e2e_value = world * B * a.steps / (e2e_ms * 1e-3)
+
+    # ---- the same batch with nothing else in flight: what one update() of 4096 problems costs alone -
+    alone = None
+    if rank == 0:
+        slot = pipe.slots[0]
+        pipe.synchronize()
+        if not a.no_graph:
+            slot.capture(resident_body)
+        one = (lambda: slot.replay()) if not a.no_graph else (lambda: resident_body(slot))
+        with torch.cuda.stream(slot.stream):
+            for _ in range(3):
+                one()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                one()
+            e1.record()
+        e1.synchronize()
+        alone_ms = e0.elapsed_time(e1) / 10
+        alone = {"ms_per_update": alone_ms, "value": B / (alone_ms * 1e-3), "unit": "solves/s",
+                 "what": "one batch of 4096, updates back to back on one stream (the headline keeps "
+                         f"{depth} such batches in flight)"}
 
     # ---- BASELINE.json configs[2]: every rank takes part (scene-sharded, one final gather) -----
     peak_fp64 = opt.measure_fp64_tflops()
@@ -563,6 +596,7 @@ def run_ours(a):
                 raise SystemExit("GPU results differ from the reference's beyond 1e-9")
             # second half of the metric: p50 latency of ONE solve (batch = 1), same problem shape
             line["latency"] = single_solve_latency(lib, pb, cpu=True)
+            line["one_batch_alone"] = alone
             if not a.skip_configs:
                 line["configs"] = {"3_multistart_65536": cfg3, "4_lateral_16384": config4_lateral(a, peak_fp64),
                                    "5_mpc_dead_time_32768": config5_mpc_dead_time(a, peak_fp64)}
