@@ -108,7 +108,8 @@ typedef struct {
                                       2 = alpha = 1, 0.1 first, the other six only for the problems that
                                           need them (least work: best when the GPU is full, i.e. large
                                           batches or several batches in flight on different streams),
-                                      0 = choose by batch size (2 from 16384 problems on). */
+                                      0 = choose by batch size (2 from 8192 problems on; from 16384 on for problem
+                                          definitions with more than 6 states or lookups in the dynamics). */
     int32_t keep_records;          /* 1: the derivative records of the last linearisation stay readable through
                                       tplb_expand_derivatives() after update().  The sequences for small
                                       batches always keep them; the fused sweep of the throughput sequence

@@ -578,7 +578,7 @@ def test_remaining_zoo_models_against_oracle(name, horizon, tol, solver_libs, or
 def test_two_round_rollouts_are_bit_identical(solver_libs):
     """`line_search_rounds` (tplb200.h): 1 rolls out all 8 step sizes at once, 2 rolls out the six
     small ones only for the problems whose alpha = 1 and 0.1 failed (pending list built with
-    atomics; the automatic choice from 16384 problems on).  Same result bit for bit."""
+    atomics; the automatic choice for large batches).  Same result bit for bit."""
     from tpl_b200 import _cabi, scenarios as sc
     pb = sc.mpc_time(batch=200, horizon=60, max_iterations=10, forced=True, seed0=777)
     out = {}

@@ -203,11 +203,15 @@ void launch_rollout(const tplb_batch& q, const tplb::Workspace& ws, cudaStream_t
 }
 
 // tplb_batch.line_search_rounds: 2 selects the throughput sequence, 1 the latency sequence,
-// 0 decides by batch size (measured on B200: 8192 and 12288 problems are faster with the
-// latency sequence, 16384 and more with the throughput sequence).
+// 0 decides by batch size.  Measured on B200, one batch alone (scripts/plan_crossover.sh): with the
+// fused sweep of round 2 the throughput sequence wins from about 8192 problems on for the models
+// whose sweep fits the register file (6x2 bicycle: 4096 problems 4.0 vs 4.4 ms, 8192 5.5 vs 4.8 ms,
+// 16384 8.8 vs 6.0 ms; lateral 2x1: even at 8192); the 7x2 model with lookups in its dynamics
+// (its fused sweep spills) still prefers the latency sequence at 8192 (15.3 vs 19.2 ms).
 bool throughput_sequence(const tplb_batch& q) {
     if (q.line_search_rounds != 0) return q.line_search_rounds == 2;
-    return q.batch >= 16384;
+    constexpr bool lean_sweep = Model::X <= 6 && Model::DYNAMICS_LOOKUPS == 0;
+    return q.batch >= (lean_sweep ? 8192 : 16384);
 }
 
 template <typename R>
