@@ -186,7 +186,7 @@ template <typename R, int NA, bool kInit, bool kCost = false>
 void launch_rollout(const tplb_batch& q, const tplb::Workspace& ws, cudaStream_t st, int a_begin,
                     const int32_t* list) {
     const dim3 grid((q.batch + PB - 1) / PB), block(PB, NA);
-    const size_t smem = tplb::rollout_smem_bytes<Model, kInit, kCost>(PB);
+    const size_t smem = tplb::rollout_smem_bytes<Model, kInit, kCost>(PB, NA);
 #define TPLB_ROLLOUT(SCHEME)                                                                          \
     do {                                                                                              \
         auto kern = tplb::rollout_kernel<Model, R, PB, NA, kInit, SCHEME, kCost>;                     \

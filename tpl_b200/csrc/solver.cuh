@@ -158,6 +158,12 @@ __device__ __forceinline__ void async_copy8(double* smem_dst, const double* gmem
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
                  "l"(gmem_src));
 }
+// the same from `gmem_base` + a literal byte offset (folded into the instruction)
+template <long long kByteOffset>
+__device__ __forceinline__ void async_copy8_at(double* smem_dst, const double* gmem_base) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1+%2], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_base), "n"(kByteOffset));
+}
 __device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void async_wait_all_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
@@ -235,7 +241,7 @@ __device__ __forceinline__ void step_state(const PV& P, const R* x, const R* u, 
 //   !kInit  : line search, block = PB problems x 8 step sizes; threadIdx.x = problem
 //             (coalesced), threadIdx.y = i with alpha_i = 1 / 10^i (optim.c:863);
 //             candidates go to ws.cand_x / ws.cand_u (the reference's next_x / next_u)
-// Dynamic shared memory: rollout_smem_bytes<M, kInit>(PB) (input staging, shared by a problem's candidates).
+// Dynamic shared memory: rollout_smem_bytes<M, kInit, kCost>(PB, NA) (input staging, shared by a problem's candidates).
 // ---------------------------------------------------------------------------------
 // number of doubles one rollout stage reads per thread
 template <typename M, bool kInit, bool kCost = false>
@@ -247,12 +253,24 @@ struct RolloutInputs {
                          COUNT = O_LAM + (kCost ? M::C : 0);   // kCost: the multipliers of the stage cost
 };
 
-constexpr int kRolloutSlots = 3;                             // stages in flight in the staging ring
+// Batch sizes that get their own copy of the two hot kernel bodies with the batch size as a literal
+// (BASELINE.json's 4096, 32768 and 65536): every component stride i * B * 8 then is an immediate of
+// the load / store / copy instruction instead of 64-bit address arithmetic (sweep: 1461 -> 1190
+// instructions per stage, first rollout round: 823 -> 658).  Any other size runs the general body.
+constexpr int kSpecialBatch0 = 4096, kSpecialBatch1 = 32768, kSpecialBatch2 = 65536;
+// Slots of the staging ring.  Three: the copy of stage t+2 can never overwrite what a slower warp
+// still reads for stage t.  Two, with a second barrier at the end of every stage, for the first
+// line-search round of the throughput sequence (2 step sizes = 2 warps per block, where the barrier
+// is cheap): that kernel runs 8 blocks per multiprocessor, and 8 x 23 KB of staging would leave the
+// co-resident sweep too little L1 for its loads in flight (measured: -10 %; with two slots +5 %).
+__host__ __device__ constexpr int rollout_slots(int step_sizes, bool with_cost) {
+    return (step_sizes == 2 && with_cost) ? 2 : 3;
+}
 
 template <typename M, bool kInit, bool kCost = false>
-__host__ __device__ inline size_t rollout_smem_bytes(int problems_per_block) {
+__host__ __device__ inline size_t rollout_smem_bytes(int problems_per_block, int step_sizes) {
     using RI = RolloutInputs<M, kInit, kCost>;
-    return sizeof(double) * kRolloutSlots * RI::COUNT * problems_per_block;
+    return sizeof(double) * rollout_slots(step_sizes, kCost) * RI::COUNT * problems_per_block;
 }
 
 // global address of staged item E at stage t for problem b (scene for the stage constants)
@@ -272,21 +290,41 @@ __device__ __forceinline__ const double* rollout_source(const tplb_batch& q, con
     else return q.lagrange_multiplier + (t * C + (E - RI::O_LAM)) * B + b;
 }
 
+// The same address split into the first item of E's array at stage t (one computation per array,
+// stage and thread) and E's position behind it in units of the batch stride: with a literal batch
+// size KB the position is a literal byte offset of the copy instruction.  The stage constants
+// are strided by the number of scenes and keep the general form.
+template <typename M, bool kInit, bool kCost, int E>
+struct RolloutItem {
+    using RI = RolloutInputs<M, kInit, kCost>;
+    static constexpr bool kBatchStrided = !(E >= RI::O_SC && E < RI::O_LAM);
+    static constexpr int kFirst = E < RI::O_K ? RI::O_U : E < RI::O_HI ? RI::O_K : E < RI::O_LO ? RI::O_HI
+                                : E < RI::O_KK ? RI::O_LO : E < RI::O_X ? RI::O_KK : E < RI::O_SC ? RI::O_X
+                                : E < RI::O_LAM ? RI::O_SC : RI::O_LAM;
+    static constexpr int kIndex = E - kFirst;
+};
+
 // copies items [E0, E1) of stage t into the ring slot `dst` (this problem's column)
 // (`skip_lam`: the multipliers are known to be 0 and their ring entries were zeroed once)
-template <typename M, bool kInit, bool kCost, int PB, int E0, int E1>
+template <typename M, bool kInit, bool kCost, int PB, int E0, int E1, int KB = 0>
 __device__ __forceinline__ void rollout_fetch_range(const tplb_batch& q, const Workspace& ws, size_t t, int b,
                                                     int scene, double* dst, bool skip_lam) {
     if constexpr (E0 < E1) {
-        if (E0 < RolloutInputs<M, kInit, kCost>::O_LAM || !skip_lam)
-            async_copy8(dst + E0 * PB, rollout_source<M, kInit, kCost, E0>(q, ws, t, b, scene));
-        rollout_fetch_range<M, kInit, kCost, PB, E0 + 1, E1>(q, ws, t, b, scene, dst, skip_lam);
+        using Item = RolloutItem<M, kInit, kCost, E0>;
+        if (E0 < RolloutInputs<M, kInit, kCost>::O_LAM || !skip_lam) {
+            if constexpr (KB > 0 && Item::kBatchStrided)
+                async_copy8_at<(long long)Item::kIndex * KB * 8>(
+                    dst + E0 * PB, rollout_source<M, kInit, kCost, Item::kFirst>(q, ws, t, b, scene));
+            else
+                async_copy8(dst + E0 * PB, rollout_source<M, kInit, kCost, E0>(q, ws, t, b, scene));
+        }
+        rollout_fetch_range<M, kInit, kCost, PB, E0 + 1, E1, KB>(q, ws, t, b, scene, dst, skip_lam);
     }
 }
 
 // candidate R of NA copies the R-th chunk of the items; `yy` is uniform in a warp, so the
 // chain of comparisons is a uniform jump and every warp issues only its own copies
-template <typename M, bool kInit, bool kCost, int PB, int NA, int R = 0>
+template <typename M, bool kInit, bool kCost, int PB, int NA, int KB = 0, int R = 0>
 __device__ __forceinline__ void rollout_fetch(const tplb_batch& q, const Workspace& ws, size_t t, int b, int scene,
                                               double* dst, int yy, bool skip_lam) {
     using RI = RolloutInputs<M, kInit, kCost>;
@@ -294,17 +332,17 @@ __device__ __forceinline__ void rollout_fetch(const tplb_batch& q, const Workspa
     if constexpr (R < NA) {
         if (yy == R) {
             constexpr int E0 = R * CH, E1 = (R + 1) * CH < RI::COUNT ? (R + 1) * CH : RI::COUNT;
-            rollout_fetch_range<M, kInit, kCost, PB, (E0 < RI::COUNT ? E0 : RI::COUNT), E1>(q, ws, t, b, scene, dst,
-                                                                                         skip_lam);
+            rollout_fetch_range<M, kInit, kCost, PB, (E0 < RI::COUNT ? E0 : RI::COUNT), E1, KB>(q, ws, t, b, scene,
+                                                                                             dst, skip_lam);
         } else {
-            rollout_fetch<M, kInit, kCost, PB, NA, R + 1>(q, ws, t, b, scene, dst, yy, skip_lam);
+            rollout_fetch<M, kInit, kCost, PB, NA, KB, R + 1>(q, ws, t, b, scene, dst, yy, skip_lam);
         }
     }
 }
 
 // One thread = one (problem, step size); block = PB problems (threadIdx.x) x NA step sizes.
 // All step sizes of a problem read the same inputs (u, k, bounds, K, x, stage constants of
-// stage t), so the block stages them ONCE per problem: `smem` is a ring of kRolloutSlots
+// stage t), so the block stages them ONCE per problem: `smem` is a ring of rollout_slots()
 // stages, [slot][COUNT][PB] doubles.  The candidates of a problem share the copies of a stage
 // (each a contiguous chunk of the items), asynchronously and one stage ahead; one
 // __syncthreads per stage publishes them.  With three slots the copy of stage t+2 can never
@@ -313,11 +351,13 @@ __device__ __forceinline__ void rollout_fetch(const tplb_batch& q, const Workspa
 // kCost: the thread also evaluates the stage costs of its candidate and adds them up in the
 // reference's order (optim.c:773-790) -> ws.cand_cost; used when the GPU is full, where
 // re-reading the candidates in a separate cost kernel costs more than the longer chain.
-template <typename M, typename R, int PB, int NA, bool kInit, int kScheme, bool kCost>
+template <typename M, typename R, int PB, int NA, bool kInit, int kScheme, bool kCost, int KB = 0>
 __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace& ws, int b, int ai, bool live,
                                             unsigned char* smem) {
+    if constexpr (KB > 0) __builtin_assume(q.batch == KB);
     using D = Dims<M>;
     using RI = RolloutInputs<M, kInit, kCost>;
+    constexpr int kSlots = rollout_slots(NA, kCost);
     constexpr int X = D::X, U = D::U, NSC = D::NSC;
     const int B = q.batch;
     const int px = threadIdx.x, yy = threadIdx.y;
@@ -353,11 +393,11 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
     auto ring = [&](int buf) { return stage_in + buf * (RI::COUNT * PB); };
     const bool skip_lam = kCost && D::C > 0 && live && ws.lam_zero[b] != 0;
     auto fetch = [&](int t, int buf) {
-        rollout_fetch<M, kInit, kCost, PB, NA>(q, ws, (size_t)t, b, scene, ring(buf), yy, skip_lam);
+        rollout_fetch<M, kInit, kCost, PB, NA, KB>(q, ws, (size_t)t, b, scene, ring(buf), yy, skip_lam);
     };
     if (kCost && skip_lam && yy == 0) {                      // the first barrier of the loop publishes the zeros
 #pragma unroll
-        for (int sl = 0; sl < kRolloutSlots; ++sl)
+        for (int sl = 0; sl < kSlots; ++sl)
 #pragma unroll
             for (int cc = 0; cc < D::C; ++cc) ring(sl)[(RI::O_LAM + cc) * PB] = 0.0;
     }
@@ -381,7 +421,7 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
     async_commit();
     int buf = 0;
     for (int t = 0; t < T; ++t) {
-        const int nxt = buf + 1 == kRolloutSlots ? 0 : buf + 1;
+        const int nxt = buf + 1 == kSlots ? 0 : buf + 1;
         if (live && t + 1 < Tb) fetch(t + 1, nxt);
         async_commit();                                      // (possibly empty) group of stage t+1
         async_wait_all_but_one();                            // this thread's share of stage t has landed
@@ -431,6 +471,7 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
             }
         }
         buf = nxt;
+        if constexpr (kSlots == 2) __syncthreads();   // two slots: nobody may still read the slot the next fetch fills
     }
     if (kCost && live) {
         R sc[D::NSCs], c;
@@ -443,14 +484,25 @@ __device__ __forceinline__ void dev_rollout(const tplb_batch& q, const Workspace
 
 // NA: step sizes per problem in this launch = blockDim.y (1 initial rollout, 8 all at once, 2 / 6 the
 // two rounds of the throughput sequence)
+// The first line-search round of the throughput sequence is built for 8 blocks of 64 threads per
+// multiprocessor (128 registers; no spills up to 6 states): measured best together with the
+// two-slot ring — 6 blocks (158 registers) and 10 blocks (96 registers) are both slower.
 template <typename M, typename R, int PB, int NA, bool kInit, int kScheme, bool kCost = false>
-__global__ void __launch_bounds__(PB * NA)
+__global__ void __launch_bounds__(PB * NA, (NA == 2 && kCost && M::X <= 6) ? 8 : 1)
 rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int a_begin, const int32_t* list) {
     extern __shared__ __align__(16) unsigned char rollout_smem[];
     const int ai = kInit ? 0 : a_begin + threadIdx.y;
     if (list && blockIdx.x * PB >= *ws.pending_count) return;   // block-uniform: nothing pending here
     const int b = problem_of(list, ws.pending_count, blockIdx.x * PB + threadIdx.x, q.batch);
-    dev_rollout<M, R, PB, NA, kInit, kScheme, kCost>(q, ws, b < 0 ? 0 : b, ai, b >= 0, rollout_smem);
+    const int bb = b < 0 ? 0 : b;
+    if (kCost && NA == 2 && q.batch == kSpecialBatch0)          // literal batch size, see kSpecialBatch0
+        dev_rollout<M, R, PB, NA, kInit, kScheme, kCost, kSpecialBatch0>(q, ws, bb, ai, b >= 0, rollout_smem);
+    else if (kCost && NA == 2 && q.batch == kSpecialBatch1)
+        dev_rollout<M, R, PB, NA, kInit, kScheme, kCost, kSpecialBatch1>(q, ws, bb, ai, b >= 0, rollout_smem);
+    else if (kCost && NA == 2 && q.batch == kSpecialBatch2)
+        dev_rollout<M, R, PB, NA, kInit, kScheme, kCost, kSpecialBatch2>(q, ws, bb, ai, b >= 0, rollout_smem);
+    else
+        dev_rollout<M, R, PB, NA, kInit, kScheme, kCost>(q, ws, bb, ai, b >= 0, rollout_smem);
 }
 
 // ---------------------------------------------------------------------------------
@@ -1044,8 +1096,9 @@ __device__ __forceinline__ void stage_record(const PV& P, const R* x, const R* u
         if (M::deriv_owner(e)) rec[M::deriv_slot(e)] = blk[e];
 }
 
-template <typename M, typename R>
+template <typename M, typename R, int KB = 0>
 __device__ __forceinline__ void dev_sweep(const tplb_batch& q, const Workspace& ws, int b, int iteration) {
+    if constexpr (KB > 0) __builtin_assume(q.batch == KB);
     using D = Dims<M>;
     using S = double;                            // line-search candidates are fp64 in every mode
     using SR = scratch_t<R>;                     // derivative records: storage type of the compute precision
@@ -1208,7 +1261,10 @@ sweep_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteration) 
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b == 0) *ws.pending_count = 0;           // the line search of this iteration starts empty
     if (b >= q.batch) return;
-    dev_sweep<M, R>(q, ws, b, iteration);
+    if (q.batch == kSpecialBatch0) dev_sweep<M, R, kSpecialBatch0>(q, ws, b, iteration);   // literal batch size
+    else if (q.batch == kSpecialBatch1) dev_sweep<M, R, kSpecialBatch1>(q, ws, b, iteration);
+    else if (q.batch == kSpecialBatch2) dev_sweep<M, R, kSpecialBatch2>(q, ws, b, iteration);
+    else dev_sweep<M, R>(q, ws, b, iteration);
 }
 
 // gradient-only sweep (optim.c:1038-1076): costate recursion, clipped descent direction
