@@ -254,10 +254,11 @@ struct RolloutInputs {
 };
 
 // Batch sizes that get their own copy of the two hot kernel bodies with the batch size as a literal
-// (BASELINE.json's 4096, 32768 and 65536): every component stride i * B * 8 then is an immediate of
+// (BASELINE.json's 4096, 16384, 32768 and 65536, and the 8192 of its scene-sharded multi-start): every component stride i * B * 8 then is an immediate of
 // the load / store / copy instruction instead of 64-bit address arithmetic (sweep: 1461 -> 1190
 // instructions per stage, first rollout round: 823 -> 658).  Any other size runs the general body.
-constexpr int kSpecialBatch0 = 4096, kSpecialBatch1 = 32768, kSpecialBatch2 = 65536;
+constexpr int kSpecialBatch0 = 4096, kSpecialBatch1 = 32768, kSpecialBatch2 = 65536, kSpecialBatch3 = 8192,
+              kSpecialBatch4 = 16384;
 // Slots of the staging ring.  Three: the copy of stage t+2 can never overwrite what a slower warp
 // still reads for stage t.  Two, with a second barrier at the end of every stage, for the first
 // line-search round of the throughput sequence (2 step sizes = 2 warps per block, where the barrier
@@ -501,6 +502,10 @@ rollout_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int a_begin, 
         dev_rollout<M, R, PB, NA, kInit, kScheme, kCost, kSpecialBatch1>(q, ws, bb, ai, b >= 0, rollout_smem);
     else if (kCost && NA == 2 && q.batch == kSpecialBatch2)
         dev_rollout<M, R, PB, NA, kInit, kScheme, kCost, kSpecialBatch2>(q, ws, bb, ai, b >= 0, rollout_smem);
+    else if (kCost && NA == 2 && q.batch == kSpecialBatch3)
+        dev_rollout<M, R, PB, NA, kInit, kScheme, kCost, kSpecialBatch3>(q, ws, bb, ai, b >= 0, rollout_smem);
+    else if (kCost && NA == 2 && q.batch == kSpecialBatch4)
+        dev_rollout<M, R, PB, NA, kInit, kScheme, kCost, kSpecialBatch4>(q, ws, bb, ai, b >= 0, rollout_smem);
     else
         dev_rollout<M, R, PB, NA, kInit, kScheme, kCost>(q, ws, bb, ai, b >= 0, rollout_smem);
 }
@@ -1264,6 +1269,8 @@ sweep_kernel(const __grid_constant__ tplb_batch q, Workspace ws, int iteration) 
     if (q.batch == kSpecialBatch0) dev_sweep<M, R, kSpecialBatch0>(q, ws, b, iteration);   // literal batch size
     else if (q.batch == kSpecialBatch1) dev_sweep<M, R, kSpecialBatch1>(q, ws, b, iteration);
     else if (q.batch == kSpecialBatch2) dev_sweep<M, R, kSpecialBatch2>(q, ws, b, iteration);
+    else if (q.batch == kSpecialBatch3) dev_sweep<M, R, kSpecialBatch3>(q, ws, b, iteration);
+    else if (q.batch == kSpecialBatch4) dev_sweep<M, R, kSpecialBatch4>(q, ws, b, iteration);
     else dev_sweep<M, R>(q, ws, b, iteration);
 }
 
