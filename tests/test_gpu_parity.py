@@ -597,6 +597,24 @@ def test_two_round_rollouts_are_bit_identical(solver_libs):
         q.update()
 
 
+def test_literal_batch_bodies_match_the_general_body(solver_libs):
+    """The sweep and the first rollout round carry a second copy of their body for the batch sizes
+    4096 / 8192 / 16384 / 32768 / 65536, with the batch stride as a literal (solver.cuh,
+    kSpecialBatch*): same arithmetic, so a batch of 4096 gives bit for bit what the same problems
+    give as the first 4096 of a batch of 4097 (general body)."""
+    from tpl_b200 import scenarios as sc
+    out = {}
+    for batch in (4096, 4097):
+        pb = sc.mpc_time(batch=batch, horizon=40, max_iterations=6, forced=True, seed0=31000)
+        q = sc.apply_to_batched(_factory(solver_libs, pb)(), pb)
+        q.line_search_rounds = 2
+        q.update()
+        torch.cuda.synchronize()
+        out[batch] = (q.x[:4096].clone(), q.u[:4096].clone(), q.traj_costs[:4096].clone(), q.mu_step[:4096].clone())
+    for a, b in zip(out[4096], out[4097]):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("model,kw,tol", [
     ("mpc_time", dict(batch=37, horizon=60, max_iterations=10, forced=True, seed0=900), 0.0),    # HEUN, warp-cooperative Riccati
     ("mpc", dict(batch=9, horizon=60, max_iterations=5, forced=True, seed0=910), 1e-5),          # 7 x 2, finite-difference lookups
