@@ -254,9 +254,11 @@ struct RolloutInputs {
 };
 
 // Batch sizes that get their own copy of the two hot kernel bodies with the batch size as a literal
-// (BASELINE.json's 4096, 16384, 32768 and 65536, and the 8192 of its scene-sharded multi-start): every component stride i * B * 8 then is an immediate of
-// the load / store / copy instruction instead of 64-bit address arithmetic (sweep: 1461 -> 1190
-// instructions per stage, first rollout round: 823 -> 658).  Any other size runs the general body.
+// (BASELINE.json's 4096, 16384, 32768 and 65536, and the 8192 of its scene-sharded multi-start):
+// every component stride i * B * 8 then is an immediate of the load / store / copy instruction
+// instead of 64-bit address arithmetic (sweep: 1461 -> 1190 instructions per stage, first rollout
+// round: 823 -> 658).  Any other size runs the general body; the results are bit-identical
+// (tests/test_gpu_parity.py::test_literal_batch_bodies_match_the_general_body).
 constexpr int kSpecialBatch0 = 4096, kSpecialBatch1 = 32768, kSpecialBatch2 = 65536, kSpecialBatch3 = 8192,
               kSpecialBatch4 = 16384;
 // Slots of the staging ring.  Three: the copy of stage t+2 can never overwrite what a slower warp
@@ -347,7 +349,7 @@ __device__ __forceinline__ void rollout_fetch(const tplb_batch& q, const Workspa
 // stages, [slot][COUNT][PB] doubles.  The candidates of a problem share the copies of a stage
 // (each a contiguous chunk of the items), asynchronously and one stage ahead; one
 // __syncthreads per stage publishes them.  With three slots the copy of stage t+2 can never
-// overwrite what a slower warp still reads for stage t.  `live` == false: the thread only
+// overwrite what a slower warp still reads for stage t; with two, a second barrier ends the stage.  `live` == false: the thread only
 // keeps the barriers.
 // kCost: the thread also evaluates the stage costs of its candidate and adds them up in the
 // reference's order (optim.c:773-790) -> ws.cand_cost; used when the GPU is full, where
