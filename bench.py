@@ -549,6 +549,8 @@ def run_ours(a):
                 "workload": workload_name(B, T, I),
                 "problems_per_gpu": B, "stages": T, "iterations": I, "batches_in_flight": depth,
                 "cuda_graph_per_slot": not a.no_graph,
+                "kernel_bodies": ("literal batch stride" if B in (4096, 8192, 16384, 32768, 65536) else "general")
+                                 + " (solver.cuh kSpecialBatch*: same arithmetic, bit-identical results)",
                 "line_search_rounds": a.line_search_rounds,
                 "keep_previous": False, "keep_records": False,
                 "timed_region": f"{a.steps} steps after {max(a.warmup, 2 * depth)} warm-up steps; includes filling and "
